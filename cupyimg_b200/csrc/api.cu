@@ -1,0 +1,365 @@
+// api.cu — the extern "C" boundary declared in include/sepfilt.h: argument validation,
+// geometry normalisation and kernel dispatch.  No device allocation, no retained
+// pointers, all launches on the caller's stream.
+#include <cfloat>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "common.cuh"
+#include "kernels.h"
+
+using namespace sepfilt;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const char* fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return code;
+}
+
+int fail_cuda(cudaError_t e, const char* what)
+{
+    return fail(SEPFILT_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+}
+
+struct DeviceGuard {
+    int prev = -1;
+    bool switched = false;
+    cudaError_t err = cudaSuccess;
+    explicit DeviceGuard(int dev)
+    {
+        err = cudaGetDevice(&prev);
+        if (err == cudaSuccess && prev != dev) {
+            err = cudaSetDevice(dev);
+            switched = (err == cudaSuccess);
+        }
+    }
+    ~DeviceGuard() { if (switched) cudaSetDevice(prev); }
+};
+
+bool valid_dtype(int t) { return t >= SEPFILT_I8 && t <= SEPFILT_BOOL; }
+
+int check_tensor(const sepfilt_tensor* t, const char* name, bool is_output)
+{
+    if (!t) return fail(SEPFILT_ERR_INVALID, "%s tensor is NULL", name);
+    if (t->ndim < 0 || t->ndim > SEPFILT_MAX_NDIM)
+        return fail(SEPFILT_ERR_INVALID, "%s rank %d out of range", name, t->ndim);
+    if (!valid_dtype(t->dtype) || (is_output && t->dtype == SEPFILT_BOOL))
+        return fail(SEPFILT_ERR_INVALID, "%s dtype %d not supported", name, t->dtype);
+    for (int d = 0; d < t->ndim; ++d)
+        if (t->shape[d] < 0) return fail(SEPFILT_ERR_INVALID, "%s has a negative extent", name);
+    return SEPFILT_OK;
+}
+
+int64_t numel(const sepfilt_tensor* t)
+{
+    int64_t n = 1;
+    for (int d = 0; d < t->ndim; ++d) n *= t->shape[d];
+    return n;
+}
+
+bool c_contiguous(const sepfilt_tensor* t)
+{
+    int64_t expect = dtype_size(t->dtype);
+    for (int d = t->ndim - 1; d >= 0; --d) {
+        if (t->shape[d] != 1 && t->stride_bytes[d] != expect) return false;
+        expect *= t->shape[d];
+    }
+    return true;
+}
+
+int check_pass(const sepfilt_pass* p, int ndim)
+{
+    if (!p) return fail(SEPFILT_ERR_INVALID, "pass is NULL");
+    if (p->axis < 0 || p->axis >= ndim) return fail(SEPFILT_ERR_INVALID, "invalid axis %d", p->axis);
+    if (p->ntaps < 1 || p->ntaps > SEPFILT_MAX_TAPS)
+        return fail(SEPFILT_ERR_INVALID, "filter length %d not in 1..%d", p->ntaps, SEPFILT_MAX_TAPS);
+    const int before = p->ntaps / 2 + p->origin;
+    if (before < 0 || before >= p->ntaps) return fail(SEPFILT_ERR_INVALID, "invalid origin");
+    if (p->mode < SEPFILT_REFLECT || p->mode > SEPFILT_WRAP)
+        return fail(SEPFILT_ERR_INVALID, "boundary mode not supported");
+    if (!p->uniform && !p->taps) return fail(SEPFILT_ERR_INVALID, "no filter weights given");
+    return SEPFILT_OK;
+}
+
+// taps of one pass as offsets -R..R around the output position, rounded to f32
+bool pass_to_f32_taps(const sepfilt_pass* p, F32Taps* t)
+{
+    const int before = p->ntaps / 2 + p->origin;
+    const int after = p->ntaps - 1 - before;
+    const int R = before > after ? before : after;
+    if (R > SEPFILT_FAST_MAX_RADIUS) return false;
+    t->radius = R;
+    for (int k = 0; k <= 2 * SEPFILT_FAST_MAX_RADIUS; ++k) t->w[k] = 0.f;
+    for (int k = 0; k < p->ntaps; ++k)
+        t->w[k - before + R] = p->uniform ? (float)(1.0 / p->ntaps) : (float)p->taps[k];
+    return true;
+}
+
+// scipy's NI_Correlate1D symmetry probe
+int probe_symmetry(const double* w, int K)
+{
+    if (!(K & 1)) return 0;
+    const int s1 = K / 2;
+    bool sym = true;
+    for (int i = 1; i <= s1; ++i)
+        if (std::fabs(w[s1 + i] - w[s1 - i]) > DBL_EPSILON) { sym = false; break; }
+    if (sym) return 1;
+    for (int i = 1; i <= s1; ++i)
+        if (std::fabs(w[s1 + i] + w[s1 - i]) > DBL_EPSILON) return 0;
+    return -1;
+}
+
+}  // namespace
+
+extern "C" {
+
+int sepfilt_version(void) { return SEPFILT_VERSION; }
+
+const char* sepfilt_last_error(void) { return g_last_error.c_str(); }
+
+int sepfilt_correlate1d(const sepfilt_tensor* in, const sepfilt_tensor* out,
+                        const sepfilt_pass* pass, int64_t in_offset, double cval,
+                        int acc, void* scratch, size_t scratch_bytes, void* stream)
+{
+    int rc;
+    if ((rc = check_tensor(in, "input", false)) || (rc = check_tensor(out, "output", true))) return rc;
+    if (in->ndim != out->ndim) return fail(SEPFILT_ERR_INVALID, "input and output rank differ");
+    if (in->ndim < 1) return fail(SEPFILT_ERR_INVALID, "rank must be >= 1");
+    if ((rc = check_pass(pass, in->ndim))) return rc;
+    for (int d = 0; d < in->ndim; ++d)
+        if (d != pass->axis && in->shape[d] != out->shape[d])
+            return fail(SEPFILT_ERR_INVALID, "output shape not correct");
+    if (in->device != out->device) return fail(SEPFILT_ERR_INVALID, "input and output on different devices");
+    if (acc != SEPFILT_ACC_F64_EXACT && acc != SEPFILT_ACC_F32)
+        return fail(SEPFILT_ERR_INVALID, "unknown accumulator policy %d", acc);
+    const int64_t total = numel(out);
+    if (total == 0) return SEPFILT_OK;
+    if (in->shape[pass->axis] < 1) return fail(SEPFILT_ERR_INVALID, "input is empty along the filtered axis");
+    if (!in->ptr || !out->ptr) return fail(SEPFILT_ERR_INVALID, "NULL data pointer");
+
+    DeviceGuard guard(in->device);
+    if (guard.err != cudaSuccess) return fail_cuda(guard.err, "cudaSetDevice");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const int axis = pass->axis;
+
+    if (acc == SEPFILT_ACC_F32) {
+        if (in->dtype != SEPFILT_F32 || out->dtype != SEPFILT_F32)
+            return fail(SEPFILT_ERR_UNSUPPORTED, "float32 accumulation needs float32 input and output");
+        if (!c_contiguous(in) || !c_contiguous(out))
+            return fail(SEPFILT_ERR_UNSUPPORTED, "float32 tiled pass needs C-contiguous arrays");
+        F32Taps taps;
+        if (!pass_to_f32_taps(pass, &taps))
+            return fail(SEPFILT_ERR_UNSUPPORTED, "filter radius exceeds %d", SEPFILT_FAST_MAX_RADIUS);
+        if (in->shape[axis] > 2147483647LL - 64 || out->shape[axis] > 2147483647LL - 64 ||
+            in_offset > 2147483647LL / 2 || in_offset < -2147483647LL / 2)
+            return fail(SEPFILT_ERR_UNSUPPORTED, "axis too long for the tiled pass");
+        F32Line g;
+        g.in = static_cast<const float*>(in->ptr);
+        g.out = static_cast<float*>(out->ptr);
+        g.outer = 1;
+        g.inner = 1;
+        for (int d = 0; d < axis; ++d) g.outer *= in->shape[d];
+        for (int d = axis + 1; d < in->ndim; ++d) g.inner *= in->shape[d];
+        g.n_in = (int32_t)in->shape[axis];
+        g.n_out = (int32_t)out->shape[axis];
+        g.in_offset = (int32_t)in_offset;
+        g.mode = pass->mode;
+        g.cval = (float)cval;
+        if (!f32_line_supported(g, taps.radius))
+            return fail(SEPFILT_ERR_UNSUPPORTED, "geometry not supported by the tiled pass");
+        cudaError_t e = launch_f32_corr1d(g, taps, s);
+        if (e != cudaSuccess) return fail_cuda(e, "corr1d_f32 launch");
+        return SEPFILT_OK;
+    }
+
+    // ---- exact path ----
+    ExactParams p;
+    std::memset(&p, 0, sizeof p);
+    p.in = static_cast<const char*>(in->ptr);
+    p.out = static_cast<char*>(out->ptr);
+    p.in_dtype = in->dtype;
+    p.out_dtype = out->dtype;
+    p.n_in = in->shape[axis];
+    p.in_offset = in_offset;
+    p.total = total;
+    p.K = pass->ntaps;
+    p.before = pass->ntaps / 2 + pass->origin;
+    p.mode = pass->mode;
+    p.cval = cval;
+    // collapse: drop unit dims, merge neighbours that are jointly contiguous in both arrays
+    int nd = 0;
+    p.axis = -1;
+    for (int d = 0; d < in->ndim; ++d) {
+        const bool is_axis = (d == axis);
+        if (!is_axis && out->shape[d] == 1) continue;
+        if (nd > 0 && !is_axis && p.axis != nd - 1 &&
+            p.istride[nd - 1] == in->stride_bytes[d] * out->shape[d] &&
+            p.ostride[nd - 1] == out->stride_bytes[d] * out->shape[d]) {
+            p.shape[nd - 1] *= out->shape[d];
+            p.istride[nd - 1] = in->stride_bytes[d];
+            p.ostride[nd - 1] = out->stride_bytes[d];
+            continue;
+        }
+        p.shape[nd] = out->shape[d];
+        p.istride[nd] = in->stride_bytes[d];
+        p.ostride[nd] = out->stride_bytes[d];
+        if (is_axis) p.axis = nd;
+        ++nd;
+    }
+    p.ndim = nd;
+    if (pass->uniform) {
+        p.symmetric = 2;
+    } else {
+        p.symmetric = probe_symmetry(pass->taps, pass->ntaps);
+        if (pass->ntaps <= SEPFILT_PARAM_TAPS) {
+            std::memcpy(p.w, pass->taps, sizeof(double) * pass->ntaps);
+        } else {
+            const size_t need = sizeof(double) * (size_t)pass->ntaps;
+            if (!scratch || scratch_bytes < need)
+                return fail(SEPFILT_ERR_SCRATCH, "filters longer than %d taps need %zu bytes of device scratch",
+                            SEPFILT_PARAM_TAPS, need);
+            cudaError_t e = cudaMemcpyAsync(scratch, pass->taps, need, cudaMemcpyHostToDevice, s);
+            if (e != cudaSuccess) return fail_cuda(e, "cudaMemcpyAsync(taps)");
+            p.wdev = static_cast<const double*>(scratch);
+        }
+    }
+    cudaError_t e = launch_exact_corr1d(p, s);
+    if (e != cudaSuccess) return fail_cuda(e, "exact_corr1d launch");
+    return SEPFILT_OK;
+}
+
+static int build_fused(const sepfilt_tensor* in, const sepfilt_tensor* out,
+                       const sepfilt_pass* passes, int npasses, const sepfilt_pass* dpasses,
+                       int gradient_magnitude, int64_t in_offset0, double cval,
+                       FusedVolume* v, F32Taps taps[3], F32Taps dtaps[3], bool set_error)
+{
+#define UNSUP(...) return set_error ? fail(SEPFILT_ERR_UNSUPPORTED, __VA_ARGS__) : SEPFILT_ERR_UNSUPPORTED
+    if (!in || !out || !passes) UNSUP("NULL argument");
+    if (in->dtype != SEPFILT_F32 || out->dtype != SEPFILT_F32) UNSUP("fused path is float32 only");
+    if (in->ndim != out->ndim || (in->ndim != 2 && in->ndim != 3)) UNSUP("fused path needs rank 2 or 3");
+    if (!c_contiguous(in) || !c_contiguous(out)) UNSUP("fused path needs C-contiguous arrays");
+    const int nd = in->ndim;
+    for (int d = 1; d < nd; ++d)
+        if (in->shape[d] != out->shape[d]) UNSUP("shape mismatch");
+    if (nd == 2 && (in_offset0 != 0 || in->shape[0] != out->shape[0])) UNSUP("windows need rank 3");
+    if (npasses < 1 || npasses > nd) UNSUP("bad pass count");
+    if (gradient_magnitude && (npasses != nd || !dpasses)) UNSUP("gradient magnitude needs one pass per axis");
+    for (int a = 0; a < 3; ++a) {
+        taps[a].radius = 0;
+        for (int k = 0; k <= 2 * SEPFILT_FAST_MAX_RADIUS; ++k) taps[a].w[k] = dtaps[a].w[k] = 0.f;
+        taps[a].w[0] = 1.f;   // identity
+        dtaps[a] = taps[a];
+        v->mode[a] = SEPFILT_NEAREST;
+    }
+    bool seen[3] = {false, false, false};
+    for (int i = 0; i < npasses; ++i) {
+        const sepfilt_pass* p = &passes[i];
+        if (p->axis < 0 || p->axis >= nd || p->ntaps < 1) UNSUP("bad pass");
+        const int before = p->ntaps / 2 + p->origin;
+        if (before < 0 || before >= p->ntaps) UNSUP("invalid origin");
+        const int a = p->axis + (3 - nd);      // slot: 0 = z, 1 = y, 2 = x
+        if (seen[a]) UNSUP("duplicate axis");
+        seen[a] = true;
+        if (!pass_to_f32_taps(p, &taps[a])) UNSUP("radius too large");
+        if (taps[a].radius > in->shape[p->axis]) UNSUP("radius exceeds the axis extent");
+        v->mode[a] = p->mode;
+        if (gradient_magnitude) {
+            const sepfilt_pass* q = &dpasses[i];
+            if (q->axis != p->axis || q->mode != p->mode) UNSUP("derivative passes must mirror the smoothing passes");
+            if (!pass_to_f32_taps(q, &dtaps[a])) UNSUP("radius too large");
+            if (dtaps[a].radius > in->shape[p->axis]) UNSUP("radius exceeds the axis extent");
+        }
+    }
+    v->in = static_cast<const float*>(in->ptr);
+    v->out = static_cast<float*>(out->ptr);
+    if (nd == 3) {
+        if (in->shape[0] > 2147483647LL || out->shape[0] > 2147483647LL) UNSUP("too many planes");
+        v->nz_in = (int32_t)in->shape[0];
+        v->nz_out = (int32_t)out->shape[0];
+        v->z_offset = (int32_t)in_offset0;
+    } else {
+        v->nz_in = v->nz_out = 1;
+        v->z_offset = 0;
+    }
+    if (in->shape[nd - 2] > 2147483647LL || in->shape[nd - 1] > 2147483647LL) UNSUP("plane too large");
+    v->ny = (int32_t)in->shape[nd - 2];
+    v->nx = (int32_t)in->shape[nd - 1];
+    v->cval = (float)cval;
+    if (!fused3d_supported(*v, taps, gradient_magnitude != 0)) UNSUP("geometry not supported by the fused kernel");
+    return SEPFILT_OK;
+#undef UNSUP
+}
+
+int sepfilt_separable_f32_supported(const sepfilt_tensor* in, const sepfilt_tensor* out,
+                                    const sepfilt_pass* passes, int npasses, int gradient_magnitude)
+{
+    FusedVolume v;
+    F32Taps taps[3], dtaps[3];
+    // derivative passes are only needed for their radius == smoothing radius here
+    return build_fused(in, out, passes, npasses, passes, gradient_magnitude, 0, 0.0, &v, taps, dtaps, false) == SEPFILT_OK;
+}
+
+int sepfilt_separable_f32(const sepfilt_tensor* in, const sepfilt_tensor* out,
+                          const sepfilt_pass* passes, int npasses,
+                          const sepfilt_pass* dpasses, int gradient_magnitude,
+                          int64_t in_offset0, double cval, void* stream)
+{
+    FusedVolume v;
+    F32Taps taps[3], dtaps[3];
+    int rc = build_fused(in, out, passes, npasses, dpasses, gradient_magnitude, in_offset0, cval,
+                         &v, taps, dtaps, true);
+    if (rc != SEPFILT_OK) return rc;
+    if (numel(out) == 0) return SEPFILT_OK;
+    DeviceGuard guard(in->device);
+    if (guard.err != cudaSuccess) return fail_cuda(guard.err, "cudaSetDevice");
+    cudaError_t e = launch_fused3d(v, taps, dtaps, gradient_magnitude != 0, static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return fail_cuda(e, "fused3d launch");
+    return SEPFILT_OK;
+}
+
+int sepfilt_gradmag_step(void* acc, const void* a, int64_t n, int dtype, int op, void* stream)
+{
+    if (n < 0 || op < 0 || op > 3 || dtype < SEPFILT_I8 || dtype > SEPFILT_F64)
+        return fail(SEPFILT_ERR_INVALID, "bad gradmag_step arguments");
+    if (n == 0) return SEPFILT_OK;
+    if (!acc || !a) return fail(SEPFILT_ERR_INVALID, "NULL data pointer");
+    cudaError_t e = launch_gradmag_step(acc, a, n, dtype, op, static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return fail_cuda(e, "gradmag_step launch");
+    return SEPFILT_OK;
+}
+
+int sepfilt_copy_cast(const sepfilt_tensor* in, const sepfilt_tensor* out, void* stream)
+{
+    // a 1-tap identity correlation is a strided copy under the store's cast rules
+    static const double one = 1.0;
+    int rc;
+    if ((rc = check_tensor(in, "input", false)) || (rc = check_tensor(out, "output", true))) return rc;
+    sepfilt_tensor i1 = *in, o1 = *out;
+    if (i1.ndim == 0) {
+        i1.ndim = o1.ndim = 1;
+        i1.shape[0] = o1.shape[0] = 1;
+        i1.stride_bytes[0] = dtype_size(i1.dtype);
+        o1.stride_bytes[0] = dtype_size(o1.dtype);
+    }
+    sepfilt_pass p;
+    std::memset(&p, 0, sizeof p);
+    p.axis = i1.ndim - 1;
+    p.ntaps = 1;
+    p.taps = &one;
+    p.mode = SEPFILT_NEAREST;
+    return sepfilt_correlate1d(&i1, &o1, &p, 0, 0.0, SEPFILT_ACC_F64_EXACT, nullptr, 0, stream);
+}
+
+}  // extern "C"

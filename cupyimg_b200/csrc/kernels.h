@@ -1,0 +1,63 @@
+// kernels.h — host-side launcher interface between api.cu and the kernel files.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/sepfilt.h"
+
+namespace sepfilt {
+
+// ---- exact path (exact.cu): float64, scipy order, any dtype pair, any strides ----
+struct ExactParams {
+    const char* in;
+    char*       out;
+    int32_t     in_dtype, out_dtype;
+    int32_t     ndim;                    // collapsed rank (>= 1), dims in C order
+    int32_t     axis;
+    int64_t     shape[SEPFILT_MAX_NDIM]; // OUTPUT extents
+    int64_t     istride[SEPFILT_MAX_NDIM];
+    int64_t     ostride[SEPFILT_MAX_NDIM];
+    int64_t     n_in;                    // input extent along axis
+    int64_t     in_offset;               // out position p <-> in position p + in_offset
+    int64_t     total;                   // number of output elements
+    int32_t     K, before;               // before = K/2 + origin
+    int32_t     mode;
+    int32_t     symmetric;               // +1 / -1 / 0 (scipy's probe), 2 = uniform window sum
+    double      cval;
+    const double* wdev;                  // taps in device memory (K > SEPFILT_PARAM_TAPS) or nullptr
+    double      w[SEPFILT_PARAM_TAPS];
+};
+cudaError_t launch_exact_corr1d(const ExactParams& p, cudaStream_t s);
+cudaError_t launch_gradmag_step(void* acc, const void* a, int64_t n, int dtype, int op, cudaStream_t s);
+
+// ---- f32 tiled 1-D passes (f32_1d.cu): C-contiguous (outer, n, inner) view ----
+struct F32Taps {
+    int32_t radius;                       // R: taps cover offsets -R..R (zero padded)
+    float   w[2 * SEPFILT_FAST_MAX_RADIUS + 1];
+};
+struct F32Line {
+    const float* in;
+    float*       out;
+    int64_t      outer;      // product of extents before the axis
+    int32_t      n_in, n_out;
+    int64_t      inner;      // product of extents after the axis (1 = contiguous axis)
+    int32_t      in_offset;
+    int32_t      mode;
+    float        cval;
+};
+bool        f32_line_supported(const F32Line& g, int radius);
+cudaError_t launch_f32_corr1d(const F32Line& g, const F32Taps& t, cudaStream_t s);
+
+// ---- fused multi-axis f32 (fused3d.cu) ----
+struct FusedVolume {
+    const float* in;
+    float*       out;
+    int32_t      nz_in, nz_out, ny, nx;   // 2-D inputs use nz = 1 with an identity z pass
+    int32_t      z_offset;                // out plane z <-> in plane z + z_offset
+    int32_t      mode[3];                 // per axis (z, y, x)
+    float        cval;
+};
+bool        fused3d_supported(const FusedVolume& v, const F32Taps taps[3], bool gradmag);
+cudaError_t launch_fused3d(const FusedVolume& v, const F32Taps taps[3], const F32Taps dtaps[3],
+                           bool gradmag, cudaStream_t s);
+
+}  // namespace sepfilt

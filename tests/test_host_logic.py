@@ -1,0 +1,94 @@
+"""Host-side logic that needs no GPU: argument validation, tap generation, aliasing
+analysis, descriptor construction."""
+import itertools
+
+import numpy as np
+import pytest
+
+from cupyimg_b200 import _array, _ffi
+from cupyimg_b200.scipy.ndimage import filters as F
+
+
+def test_gaussian_kernel_matches_scipy_bitwise():
+    from scipy.ndimage._filters import _gaussian_kernel1d
+    for sigma, order in itertools.product([0.5, 1.0, 1.5, 2.0, 4.0, 7.3], range(4)):
+        lw = int(4 * sigma + 0.5)
+        np.testing.assert_array_equal(F._gaussian_kernel1d(sigma, order, lw), _gaussian_kernel1d(sigma, order, lw))
+    with pytest.raises(ValueError):
+        F._gaussian_kernel1d(1.0, -1, 4)
+
+
+def test_origin_mode_axis_validation():
+    for width in range(1, 9):
+        lo, hi = -(width // 2), (width - 1) // 2
+        for o in range(lo, hi + 1):
+            assert F._check_origin(o, width) == o
+        for o in (lo - 1, hi + 1):
+            with pytest.raises(ValueError):
+                F._check_origin(o, width)
+    for m in ("reflect", "constant", "nearest", "mirror", "wrap", "grid-mirror", "grid-wrap", "grid-constant"):
+        assert 0 <= F._check_mode(m) <= 4
+    assert F._check_mode("grid-constant") == F._check_mode("constant")
+    assert F._check_mode("grid-wrap") == F._check_mode("wrap")
+    assert F._check_mode("grid-mirror") == F._check_mode("reflect")
+    for bad in ("", "foo", None, 3):
+        with pytest.raises(RuntimeError):
+            F._check_mode(bad)
+    assert F._normalize_axis_index(-1, 3) == 2
+    for bad in (3, -4):
+        with pytest.raises(ValueError):
+            F._normalize_axis_index(bad, 3)
+    with pytest.raises(RuntimeError):
+        F._normalize_sequence([1, 2], 3)
+    assert F._normalize_sequence("wrap", 2) == ["wrap", "wrap"]
+    with pytest.raises(ValueError):
+        F._check_dtype_mode("numpy")
+
+
+def test_pass_spec_radius():
+    s = F._PassSpec(0, np.ones(17), 0, 0)
+    assert s.radius() == 8
+    s = F._PassSpec(0, np.ones(4), -2, 0)       # taps cover offsets 0..3
+    assert s.radius() == 3
+    s = F._PassSpec(0, None, 1, 0, uniform=True, size=5)
+    assert s.radius() == 3
+    st, keep = s.struct()
+    assert st.uniform == 1 and st.ntaps == 5 and not st.taps
+
+
+def _fake(ptr, shape, strides, dtype="float32"):
+    return _array.DevArray(ptr, shape, strides, dtype, 0, None)
+
+
+def test_overlap_and_contiguity_analysis():
+    a = _fake(1000, (4, 5), (20, 4))
+    assert a.c_contiguous() and a.byte_bounds() == (1000, 1080)
+    b = _fake(1080, (4, 5), (20, 4))
+    assert not a.may_overlap(b)
+    c = _fake(1076, (2,), (4,))
+    assert a.may_overlap(c)
+    neg = _fake(1076, (4, 5), (-20, 4))          # flipped view of the same block
+    assert neg.byte_bounds() == (1016, 1096)
+    assert not neg.c_contiguous()
+    assert _fake(0, (0, 3), (12, 4)).byte_bounds() == (0, 0)
+    assert not _fake(1000, (0, 5), (20, 4)).may_overlap(a)
+    w = a.view_axis_window(0, 1, 2)
+    assert w.shape == (2, 5) and w.ptr == 1020
+    t = a.tensor()
+    assert (t.ndim, t.dtype, t.shape[1], t.stride_bytes[0]) == (2, 8, 5, 20)
+    with pytest.raises(RuntimeError):
+        _fake(0, (2,), (2,), "float16").tensor()
+
+
+def test_dtype_helpers():
+    import torch
+    assert _array.to_numpy_dtype(torch.uint16) == np.dtype("uint16")
+    assert _array.to_numpy_dtype("f4") == np.dtype("float32")
+    assert _array.to_numpy_dtype(np.int8) == np.dtype("int8")
+    assert issubclass(_array.OutputShapeError, ValueError) and issubclass(_array.OutputShapeError, RuntimeError)
+    w = _array.host_weights([1, 2, 3])
+    assert w.dtype == np.float64
+    with pytest.raises(TypeError):
+        _array.ingest(np.zeros(3))
+    with pytest.raises(TypeError):
+        _array.ingest(torch.zeros(3))

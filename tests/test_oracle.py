@@ -1,0 +1,119 @@
+"""Pins the CPU oracle: reference known-answer tables, the reference's exhaustive
+length x origin x mode sweep (tests/test_ndimage_vs_scipy.py:24-111), and scipy.ndimage
+bit-for-bit (the oracle the reference's own tests use)."""
+import itertools
+
+import numpy as np
+import pytest
+from scipy import ndimage as sndi
+
+from oracle import oracle
+from helpers import TYPES, load_kats, run_kat
+
+KATS = load_kats()
+
+
+def _oracle_call(func, x, **kw):
+    if "weights" in kw:
+        w = kw.pop("weights")
+        return getattr(oracle, func)(x, w, **kw)
+    if func == "uniform_filter1d":
+        return oracle.uniform_filter1d(x, kw.pop("size"), **kw)
+    return getattr(oracle, func)(x, **kw)
+
+
+@pytest.mark.parametrize("case", KATS, ids=[c["id"] for c in KATS])
+def test_reference_known_answers(case):
+    run_kat(case, _oracle_call)
+
+
+@pytest.mark.parametrize("mode", ["constant", "mirror", "nearest", "reflect", "wrap"])
+@pytest.mark.parametrize("len_x", [1, 2, 3, 6, 7])
+def test_length_origin_sweep_vs_scipy(mode, len_x):
+    """Every filter length up to 2*len_x+1 (multi-reflection) x every valid origin."""
+    x = np.arange(1, 1 + len_x, dtype=np.float64)
+    for len_h in range(1, 2 * len_x + 2):
+        h = np.arange(1, 1 + len_h, dtype=np.float64)
+        lo, hi = -(len_h // 2), (len_h - 1) // 2
+        for origin in range(lo, hi + 1):
+            for fn in ("correlate1d", "convolve1d"):
+                want = getattr(sndi, fn)(x, h, mode=mode, cval=0.25, origin=origin)
+                got = getattr(oracle, fn)(x, h, mode=mode, cval=0.25, origin=origin)
+                np.testing.assert_array_equal(got, want)
+        for origin in (lo - 1, hi + 1):
+            with pytest.raises(ValueError):
+                oracle.correlate1d(x, h, mode=mode, origin=origin)
+
+
+def test_remap_tables():
+    """_util.py:170-228 index rules, spelled out (d c b a | a b c d | d c b a etc.)."""
+    n = 4
+    want = {
+        "reflect": [3, 2, 1, 0, 0, 1, 2, 3, 3, 2, 1, 0],
+        "mirror": [2, 3, 2, 1, 0, 1, 2, 3, 2, 1, 0, 1],
+        "nearest": [0, 0, 0, 0, 0, 1, 2, 3, 3, 3, 3, 3],
+        "wrap": [0, 1, 2, 3, 0, 1, 2, 3, 0, 1, 2, 3],
+        "constant": [-1, -1, -1, -1, 0, 1, 2, 3, -1, -1, -1, -1],
+    }
+    for mode, row in want.items():
+        assert [oracle.remap(mode, i, n) for i in range(-4, 8)] == row
+    assert oracle.remap("mirror", -5, 1) == 0
+
+
+@pytest.mark.parametrize("t_in,t_out", list(itertools.product(TYPES, TYPES)))
+def test_dtype_matrix_bit_exact_vs_scipy(t_in, t_out):
+    rng = np.random.default_rng(hash((t_in, t_out)) % 2**32)
+    x = (rng.random((5, 7, 6)) * 100).astype(t_in)
+    taps = [oracle.gaussian_kernel1d(1.0, 0, 4), oracle.gaussian_kernel1d(1.0, 1, 4),
+            rng.standard_normal(4), np.array([1.0, 2.0, 1.0])]
+    for w, axis in itertools.product(taps, range(3)):
+        want = sndi.correlate1d(x, w, axis=axis, output=t_out, mode="mirror")
+        got = oracle.correlate1d(x, w, axis=axis, output=t_out, mode="mirror")
+        np.testing.assert_array_equal(got, want)
+
+
+@pytest.mark.parametrize("dtype", ["float32", "float64", "uint16", "int32", "uint8"])
+def test_composite_filters_bit_exact_vs_scipy(dtype):
+    rng = np.random.default_rng(7)
+    x = (rng.random((12, 17, 9)) * 200).astype(dtype)
+    for name, args, kw in [
+        ("gaussian_filter", (1.5,), {}), ("gaussian_filter", ([1.0, 0.0, 2.0],), {"order": [0, 0, 1]}),
+        ("uniform_filter", (5,), {}), ("uniform_filter", ([3, 1, 4],), {"origin": [0, 0, -1], "mode": "wrap"}),
+        ("sobel", (0,), {}), ("prewitt", (-1,), {"mode": ["reflect", "wrap", "mirror"]}),
+        ("gaussian_gradient_magnitude", (1.5,), {}),
+        ("laplace", (), {}), ("gaussian_laplace", (1.2,), {"mode": "nearest"}),
+        ("gaussian_filter1d", (2.0,), {"axis": 1, "order": 2, "mode": "constant", "cval": 3.0}),
+    ]:
+        want = getattr(sndi, name)(x, *args, **kw)
+        got = getattr(oracle, name)(x, *args, **kw)
+        np.testing.assert_array_equal(got, want, err_msg=name)
+
+
+def test_gaussian_taps_equal_scipy_and_closed_forms():
+    from scipy.ndimage._filters import _gaussian_kernel1d
+    for sigma, order in itertools.product([0.5, 1.0, 1.5, 2.0, 4.0, 7.3], range(4)):
+        lw = int(4 * sigma + 0.5)
+        np.testing.assert_array_equal(oracle.gaussian_kernel1d(sigma, order, lw),
+                                      _gaussian_kernel1d(sigma, order, lw))
+    # closed forms, reference tests/test_filters.py:61-77
+    radius, sigma = 10, 2
+    s2 = sigma * sigma
+    x = np.arange(-radius, radius + 1, dtype=np.double)
+    phi = np.exp(-0.5 * x * x / s2)
+    phi /= phi.sum()
+    np.testing.assert_allclose(phi, oracle.gaussian_kernel1d(sigma, 0, radius))
+    np.testing.assert_allclose(-phi * x / s2, oracle.gaussian_kernel1d(sigma, 1, radius))
+    np.testing.assert_allclose(phi * (x * x / s2 - 1) / s2, oracle.gaussian_kernel1d(sigma, 2, radius))
+    np.testing.assert_allclose(phi * (3 - x * x / s2) * x / (s2 * s2), oracle.gaussian_kernel1d(sigma, 3, radius))
+
+
+def test_window_semantics():
+    """out[p] <-> in[p + in_offset]: the slab-with-halo form the sharded path uses."""
+    rng = np.random.default_rng(3)
+    x = rng.random((20, 6, 5)).astype(np.float32)
+    w = oracle.gaussian_kernel1d(1.0, 0, 4)
+    full = oracle.correlate1d(x, w, axis=0)
+    ext = x[3:17]                                   # slab 7..13 with 4 halo planes either side
+    out = np.empty((6, 6, 5), np.float32)
+    oracle._line_pass(ext, out, 0, w, w.size, 0, "reflect", 0.0, in_offset=4)
+    np.testing.assert_array_equal(out, full[7:13])
