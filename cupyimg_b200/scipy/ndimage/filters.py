@@ -262,6 +262,38 @@ def _run_passes(inp, out, specs, cval, dtype_mode):
     return out
 
 
+def _run_passes_window(inp, out, specs, cval, dtype_mode, in_offset0):
+    """Like :func:`_run_passes` for an output that is a WINDOW of the input along axis 0
+    (out plane z <-> in plane z + in_offset0; the other extents match).  This is what the
+    z-slab sharding calls: halo planes are read but never written.  ``specs`` must be in
+    increasing axis order so that the axis-0 pass — the only one that sees the window — runs
+    first, which is also the reference's pass order (filters.py:777-789)."""
+    if out.size == 0:
+        return out
+    exact = dtype_mode == "ndimage"
+    if inp.may_overlap(out):
+        raise RuntimeError("windowed filtering cannot run in place")
+    if _fused_ok(inp, out, specs, exact):
+        _launch_fused(inp, out, specs, cval, in_offset0=in_offset0)
+        return out
+    specs = list(specs)
+    if not specs or specs[0].axis != 0:
+        # identity along axis 0: the window is a plain sub-view
+        inp = inp.view_axis_window(0, in_offset0, out.shape[0])
+        return _run_passes(inp, out, specs, cval, dtype_mode)
+    if any(b.axis <= a.axis for a, b in zip(specs, specs[1:])):
+        raise RuntimeError("passes must be in increasing axis order")
+    n = len(specs)
+    tmp = _array.empty(out.shape, out.dtype, out.device) if n > 1 else None
+    ring = [tmp, out] if n % 2 == 0 else [out, tmp]
+    src = inp
+    for i, spec in enumerate(specs):
+        dst = out if i == n - 1 else ring[i % 2]
+        _launch_pass(src, dst, spec, cval, exact, in_offset=in_offset0 if i == 0 else 0)
+        src = dst
+    return out
+
+
 # ----------------------------------------------------------------------------
 # public API
 # ----------------------------------------------------------------------------
