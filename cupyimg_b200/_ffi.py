@@ -93,7 +93,7 @@ def lib():
         L.sepfilt_correlate1d.restype = ci
         L.sepfilt_separable_f32.argtypes = [TP, TP, PP, ci, PP, ci, i64, dbl, vp]
         L.sepfilt_separable_f32.restype = ci
-        L.sepfilt_separable_f32_supported.argtypes = [TP, TP, PP, ci, ci]
+        L.sepfilt_separable_f32_supported.argtypes = [TP, TP, PP, ci, ci, dbl]
         L.sepfilt_separable_f32_supported.restype = ci
         L.sepfilt_gradmag_step.argtypes = [vp, vp, i64, ci, ci, vp]
         L.sepfilt_gradmag_step.restype = ci

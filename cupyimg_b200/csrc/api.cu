@@ -303,12 +303,12 @@ static int build_fused(const sepfilt_tensor* in, const sepfilt_tensor* out,
 }
 
 int sepfilt_separable_f32_supported(const sepfilt_tensor* in, const sepfilt_tensor* out,
-                                    const sepfilt_pass* passes, int npasses, int gradient_magnitude)
+                                    const sepfilt_pass* passes, int npasses, int gradient_magnitude, double cval)
 {
     FusedVolume v;
     F32Taps taps[3], dtaps[3];
     // derivative passes are only needed for their radius == smoothing radius here
-    return build_fused(in, out, passes, npasses, passes, gradient_magnitude, 0, 0.0, &v, taps, dtaps, false) == SEPFILT_OK;
+    return build_fused(in, out, passes, npasses, passes, gradient_magnitude, 0, cval, &v, taps, dtaps, false) == SEPFILT_OK;
 }
 
 int sepfilt_separable_f32(const sepfilt_tensor* in, const sepfilt_tensor* out,

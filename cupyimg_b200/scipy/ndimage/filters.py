@@ -185,7 +185,7 @@ def _copy_cast(src, dst):
     _ffi.count_launch()
 
 
-def _fused_ok(inp, out, specs, exact, gradmag=False):
+def _fused_ok(inp, out, specs, exact, cval=0.0, gradmag=False):
     if exact or inp.dtype != _F32 or out.dtype != _F32 or inp.ndim not in (2, 3):
         return False
     if not (inp.c_contiguous() and out.c_contiguous()) or inp.may_overlap(out) or inp.size == 0:
@@ -197,7 +197,7 @@ def _fused_ok(inp, out, specs, exact, gradmag=False):
     structs = [s.struct() for s in specs]
     arr = (_ffi.Pass * len(structs))(*[s[0] for s in structs])
     return bool(_ffi.lib().sepfilt_separable_f32_supported(inp.tensor(), out.tensor(), arr, len(structs),
-                                                           1 if gradmag else 0))
+                                                           1 if gradmag else 0, float(cval)))
 
 
 def _launch_fused(inp, out, specs, cval, dspecs=None, in_offset0=0):
@@ -234,7 +234,7 @@ def _run_passes(inp, out, specs, cval, dtype_mode):
         else:
             _copy_cast(inp, out)
         return out
-    if _fused_ok(inp, out, specs, exact):
+    if _fused_ok(inp, out, specs, exact, cval):
         _launch_fused(inp, out, specs, cval)
         return out
     n = len(specs)
@@ -273,7 +273,7 @@ def _run_passes_window(inp, out, specs, cval, dtype_mode, in_offset0):
     exact = dtype_mode == "ndimage"
     if inp.may_overlap(out):
         raise RuntimeError("windowed filtering cannot run in place")
-    if _fused_ok(inp, out, specs, exact):
+    if _fused_ok(inp, out, specs, exact, cval):
         _launch_fused(inp, out, specs, cval, in_offset0=in_offset0)
         return out
     specs = list(specs)
@@ -582,7 +582,7 @@ def gaussian_gradient_magnitude(input, sigma, output=None, mode="reflect", cval=
         if out.dtype == _F32:
             smooth = _gaussian_specs(inp, sigma, 0, mode, truncate)
             deriv = _gaussian_specs(inp, sigma, 1, mode, truncate)
-            if len(smooth) == ndim and _fused_ok(inp, out, smooth, False, gradmag=True):
+            if len(smooth) == ndim and _fused_ok(inp, out, smooth, False, cval, gradmag=True):
                 _launch_fused(inp, out, smooth, cval, dspecs=deriv)
                 return _array.export(out, inp)
         output = out.obj

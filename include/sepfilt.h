@@ -150,7 +150,7 @@ SEPFILT_API int sepfilt_separable_f32(const sepfilt_tensor* in, const sepfilt_te
 /* Would sepfilt_separable_f32 accept this request?  1 yes, 0 no (no error is set). */
 SEPFILT_API int sepfilt_separable_f32_supported(const sepfilt_tensor* in, const sepfilt_tensor* out,
                                     const sepfilt_pass* passes, int npasses,
-                                    int gradient_magnitude);
+                                    int gradient_magnitude, double cval);
 
 /* Elementwise epilogue helpers used by generic_gradient_magnitude on the exact path
  * (filters.py:1187-1201: multiply / += / sqrt, all in the OUTPUT dtype):

@@ -25,12 +25,13 @@ def ndi():
     return ndimage
 
 
-def assert_f32_close(got, want, rtol=1e-5, atol_scale=1e-6):
+def assert_f32_close(got, want, rtol=1e-5, atol_scale=1e-6, atol=None):
     want64 = want.astype(np.float64)
-    atol = atol_scale * max(float(np.abs(want64).max()) if want64.size else 0.0, 1e-30)
+    if atol is None:
+        atol = atol_scale * max(float(np.abs(want64).max()) if want64.size else 0.0, 1e-30)
     err = np.abs(got.astype(np.float64) - want64)
     bound = atol + rtol * np.abs(want64)
-    assert (err <= bound).all(), "max abs err %.3e (bound %.3e)" % (err.max(), bound[err.argmax()])
+    assert (err <= bound).all(), "max abs err %.3e (bound %.3e)" % (err.max(), bound.flat[err.argmax()])
 
 
 # ---------------------------------------------------------------- known answers
@@ -274,7 +275,8 @@ F32_SHAPES = [(33, 47, 70), (64, 64, 64), (5, 300), (130, 9), (1, 1, 517), (3, 1
 @pytest.mark.parametrize("shape", F32_SHAPES, ids=[str(s) for s in F32_SHAPES])
 @pytest.mark.parametrize("mode", MODES)
 def test_f32_correlate1d_all_axes(shape, mode, ndi):
-    rng = np.random.default_rng(abs(hash((shape, mode))) % 2**32)
+    import zlib
+    rng = np.random.default_rng(zlib.crc32(repr((shape, mode)).encode()))
     x = rng.random(shape).astype(np.float32)
     xd = to_device(x)
     for K, origin in [(3, 0), (5, 1), (4, -2), (17, 0), (9, -4), (33, 0), (2, 0)]:
@@ -283,7 +285,8 @@ def test_f32_correlate1d_all_axes(shape, mode, ndi):
             want = oracle.correlate1d(x, w, axis=axis, mode=mode, cval=0.75, origin=origin)
             got = to_host(ndi.correlate1d(xd, w, axis=axis, mode=mode, cval=0.75, origin=origin))
             assert got.dtype == np.float32
-            assert_f32_close(got, want)
+            # random-sign taps cancel: float32 accumulation error scales with sum|w| * max|x|, not |result|
+            assert_f32_close(got, want, atol=1e-6 * float(np.abs(w).sum()))
 
 
 @pytest.mark.parametrize("mode", MODES)
