@@ -2,7 +2,7 @@
 // once out instead of once per axis (the reference launches one ElementwiseKernel per axis
 // plus copy-backs: filters.py:651-662 / :777-789, _filters_core.py:148-155).
 //
-// One CTA owns a TX x ty column of the volume and marches along z.  Per batch of PZ input
+// One CTA owns a TX x ty column of the volume and marches along z.  Per group of G input
 // planes:
 //   stage   (TX+2HL) x (ty+2R) raw tiles -> shared memory by TMA (cp.async.bulk.tensor.3d,
 //           one box per plane, mbarrier complete_tx), issued by one thread: no address
@@ -18,9 +18,11 @@
 //           z accumulators that shift by one plane per step (acc[j] = fma(w, v, acc[j+1]),
 //           no register moves); acc[0] is a finished output voxel and is stored with a
 //           16-byte store.
-// The next batch's TMA traffic overlaps the x + z phase.  Tensor cores are
+// Raw tiles and y-filtered tiles are double buffered: the y pass of group k+1, the x + z pass of
+// group k and the TMA traffic of groups k+2 / k+3 overlap, with one CTA barrier per group.  Tensor cores are
 // deliberately not used: this is a bandwidth / FP32-issue bound stencil.
 #include <cuda.h>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "kernels.h"
@@ -29,10 +31,8 @@ namespace sepfilt {
 
 namespace {
 
-constexpr int TX = 128;     // tile width (contiguous axis)
 constexpr int TYM = 16;     // max tile rows
 constexpr int RY = 8;       // rows per y-pass register tile
-constexpr int NT = 512;     // threads per CTA
 constexpr int MAXR = SEPFILT_FAST_MAX_RADIUS;
 
 struct FusedParams {
@@ -49,15 +49,22 @@ struct FusedParams {
 
 __host__ __device__ constexpr int rup4(int r) { return (r + 3) & ~3; }
 
-template <int R> struct Cfg {
+// TX: tile width along the contiguous axis; NT = TX * TYM / 4 threads (one float4 column group x one
+// row each in the x+z pass); G: planes per pipeline group; CTAS: co-resident CTAs per SM.
+template <int R, int TX_, int G_, int CTAS_> struct Cfg {
+    static constexpr int TX = TX_, NT = TX_ * TYM / 4, CTAS = CTAS_;
     static constexpr int HL = rup4(R);                 // x halo staged (multiple of 4 floats)
     static constexpr int PITCH = TX + 2 * HL;          // floats per staged row
     static constexpr int NCG = PITCH / 4;              // float4 column groups per row
     static constexpr int RROWS = TYM + 2 * R;          // staged rows per plane
-    static constexpr int PZ = NT / (2 * NCG);          // planes per batch: 2*NCG y-items per plane
+    static constexpr int G = G_;                       // planes per group (the pipeline granule)
     static constexpr int NV = 2 * HL / 4 + 1;          // float4 loads of the x window
     static constexpr int RSLOT = (RROWS * PITCH + 31) & ~31;   // floats per raw plane slot (128 B multiple: TMA dst)
-    static constexpr size_t SMEM = sizeof(float) * ((size_t)PZ * RSLOT + (size_t)PZ * TYM * PITCH + RROWS + PITCH) + 16;
+    static constexpr int YSLOT = TYM * PITCH;          // floats per y-filtered plane
+    static constexpr int ITEMS = 2 * NCG * G;          // y-pass items (4 cols x RY rows) per group
+    // raw[2][G][RSLOT] + ybuf[2][G][YSLOT] + patch metadata[4][NT] + 2 mbarriers
+    static constexpr size_t SMEM = sizeof(float) * (2 * (size_t)G * (RSLOT + YSLOT)) + sizeof(int) * 4 * NT + 16;
+    static_assert(ITEMS <= NT, "one y-pass item per thread");
 };
 
 typedef unsigned long long u64;
@@ -114,18 +121,27 @@ __device__ __forceinline__ void tma_load_plane(void* dst, const CUtensorMap* map
         : "memory");
 }
 
-template <int R, bool HAS_Z>
-__global__ void __launch_bounds__(NT, 1)
+#ifdef SEPFILT_DEBUG_CYCLES
+} __device__ long long g_dbg_cycles[4096]; namespace {
+#endif
+
+template <int R, bool HAS_Z, class C>
+__global__ void __launch_bounds__(C::NT, C::CTAS)
 fused3d_kernel(const __grid_constant__ FusedParams p, const __grid_constant__ CUtensorMap tmap)
 {
-    using C = Cfg<R>;
-    constexpr int HL = C::HL, PITCH = C::PITCH, NCG = C::NCG, PZ = C::PZ, NV = C::NV, RSLOT = C::RSLOT;
+    constexpr int TX = C::TX, NT = C::NT, CGW = TX / 4;
+    constexpr int HL = C::HL, PITCH = C::PITCH, NCG = C::NCG, G = C::G, NV = C::NV;
+    constexpr int RSLOT = C::RSLOT, YSLOT = C::YSLOT;
     extern __shared__ __align__(128) float smem[];
-    float* raw = smem;                                   // [PZ] slots of RSLOT floats, rows x PITCH dense inside
-    float* ybuf = smem + (size_t)PZ * RSLOT;             // [PZ][TYM][PITCH]
-    uint64_t& full_bar = *reinterpret_cast<uint64_t*>(ybuf + (size_t)PZ * TYM * PITCH);
+    float* raw = smem;                                    // [2][G] plane slots, box_rows x PITCH dense in each
+    float* ybuf = smem + 2 * G * RSLOT;                   // [2][G][TYM][PITCH]
+    int* meta = reinterpret_cast<int*>(ybuf + 2 * G * YSLOT);          // [4][NT] packed patch cells
+    uint64_t* rfull = reinterpret_cast<uint64_t*>(meta + 4 * NT);      // [2] raw slot landed (TMA complete_tx)
 
     const int tid = threadIdx.x;
+#ifdef SEPFILT_DEBUG_CYCLES
+    const long long t_start = clock64();
+#endif
     int b = blockIdx.x;
     const int tile_x = b % p.tiles_x; b /= p.tiles_x;
     const int tile_y = b % p.tiles_y; b /= p.tiles_y;
@@ -136,173 +152,222 @@ fused3d_kernel(const __grid_constant__ FusedParams p, const __grid_constant__ CU
     // input planes this CTA consumes, in input coordinates
     const int p_first = zb + p.z_offset - (HAS_Z ? R : 0);
     const int n_planes = (ze - zb) + (HAS_Z ? 2 * R : 0);
-    const int n_batches = (n_planes + PZ - 1) / PZ;
+    const int n_groups = (n_planes + G - 1) / G;
     const size_t plane_elems = (size_t)p.ny * p.nx;
 
-    // ---- stage one batch: one TMA box per plane, issued by a single thread
-    auto stage = [&](int batch) {
-        const int planes = min(PZ, n_planes - batch * PZ);
-        mbar_expect_tx(&full_bar, (uint32_t)planes * (uint32_t)(p.box_rows * PITCH * sizeof(float)));
+    // ---- stage one group: one TMA box per plane into raw slot (g & 1), issued by a single thread
+    auto issue = [&](int g) {
+        const int planes = min(G, n_planes - g * G);
+        uint64_t* bar = &rfull[g & 1];
+        mbar_expect_tx(bar, (uint32_t)planes * (uint32_t)(p.box_rows * PITCH * sizeof(float)));
         for (int q = 0; q < planes; ++q) {
-            int pz = p_first + batch * PZ + q;
+            int pz = p_first + g * G + q;
             if (p.mode_z != SEPFILT_CONSTANT) pz = remap_index32(p.mode_z, pz, p.nz_in);   // constant: OOB box -> zeros
-            tma_load_plane(raw + (size_t)q * RSLOT, &tmap, x0 - HL, y0 - R, pz, &full_bar);
+            tma_load_plane(raw + ((g & 1) * G + q) * RSLOT, &tmap, x0 - HL, y0 - R, pz, bar);
         }
     };
-    // ---- patch the zero-filled cells of an edge tile from their remapped sources.
-    // Source tables are built once per CTA: for a staged row / column that lies outside the
-    // array, the staged row / column holding its remapped source (>= 0), or -2 when the source
-    // is not inside this tile (wrap, tiny arrays: fetched from global memory instead).
+
+    // ---- edge tiles: the cells TMA zero-filled are patched from their remapped sources.
+    // Every thread owns up to two fixed out-of-array column cells and two fixed out-of-array
+    // row segments for the whole march; their (destination, source) offsets inside a plane
+    // slot are packed once into shared memory, so a patch is LDS + STS per plane with
+    // immediate plane offsets.  Source 0xffff = not inside this tile (wrap, arrays smaller than
+    // the halo): fetched from global memory.
     const int oob_top = min(p.box_rows, max(0, R - y0)), oob_bot = min(p.box_rows, max(0, y0 + p.box_rows - R - p.ny));
     const int oob_left = min(PITCH, max(0, HL - x0)), oob_right = min(PITCH, max(0, x0 + TX + HL - p.nx));
     const bool patch_rows = (oob_top + oob_bot) > 0 && p.mode_y != SEPFILT_CONSTANT;
     const bool patch_cols = (oob_left + oob_right) > 0 && p.mode_x != SEPFILT_CONSTANT;
-    int* ysrc = reinterpret_cast<int*>(&full_bar + 1);        // [RROWS]
-    int* xsrc = ysrc + C::RROWS;                               // [PITCH]
-    if (patch_rows || patch_cols) {
-        for (int i = tid; i < p.box_rows; i += NT) {
-            const int m = remap_index32(p.mode_y, y0 - R + i, p.ny) - (y0 - R);
-            ysrc[i] = (m >= 0 && m < p.box_rows) ? m : -2;
-        }
-        for (int i = tid; i < PITCH; i += NT) {
-            const int m = remap_index32(p.mode_x, x0 - HL + i, p.nx) - (x0 - HL);
-            xsrc[i] = (m >= 0 && m < PITCH) ? m : -2;
+    const bool patching = patch_rows || patch_cols;
+    constexpr int NONE = -1;
+    const int rg0 = oob_left / 4, rg1 = NCG - oob_right / 4;           // in-range column groups [rg0, rg1)
+    if (patching) {
+        auto staged_row = [&](int yy) {      // staged row holding the source of row yy; -1 stays zero; -2 not in tile
+            const int gy = remap_index32(p.mode_y, y0 - R + yy, p.ny);
+            if (gy < 0) return -1;
+            const int m = gy - (y0 - R);
+            return (m >= 0 && m < p.box_rows) ? m : -2;
+        };
+        auto staged_col = [&](int c) {
+            const int gx = remap_index32(p.mode_x, x0 - HL + c, p.nx);
+            if (gx < 0) return -1;
+            const int m = gx - (x0 - HL);
+            return (m >= 0 && m < PITCH) ? m : -2;
+        };
+        constexpr int LANES = (2 * HL <= 16) ? 16 : 2 * HL;           // lanes per staged row of column cells
+        constexpr int CROWS = NT / LANES;
+        static_assert(TYM + 2 * R <= 2 * CROWS, "column cells are covered in two sweeps");
+        for (int sweep = 0; sweep < 2; ++sweep) {
+            int mc = NONE, mr = NONE;
+            const int cb = tid % LANES, nc = oob_left + oob_right, yy = tid / LANES + sweep * CROWS;
+            if (patch_cols && cb < nc && yy < p.box_rows) {
+                const int c = cb < oob_left ? cb : PITCH - oob_right + (cb - oob_left);
+                const bool row_oob = yy < oob_top || yy >= p.box_rows - oob_bot;
+                const int sy = row_oob ? staged_row(yy) : yy, sx = staged_col(c);
+                if (sy != -1 && sx != -1)
+                    mc = (yy * PITCH + c) | (((sy >= 0 && sx >= 0) ? sy * PITCH + sx : 0xffff) << 16);
+            }
+            const int ra = (tid >> 5) + sweep * (NT / 32);
+            if (patch_rows && ra < oob_top + oob_bot) {
+                const int ry = ra < oob_top ? ra : p.box_rows - oob_bot + (ra - oob_top);
+                const int sy = staged_row(ry);
+                if (sy != -1) mr = (ry * PITCH) | ((sy >= 0 ? sy * PITCH : 0xffff) << 16);
+            }
+            meta[sweep * NT + tid] = mc;
+            meta[(2 + sweep) * NT + tid] = mr;
         }
     }
-    auto global_cell = [&](int batch, int q, int yy, int c) -> float {
-        const int pz = remap_index32(p.mode_z, p_first + batch * PZ + q, p.nz_in);
+    auto global_cell = [&](int g, int q, int off) -> float {
+        const int yy = off / PITCH, c = off - yy * PITCH;
+        const int pz = remap_index32(p.mode_z, p_first + g * G + q, p.nz_in);
         const int gy = remap_index32(p.mode_y, y0 - R + yy, p.ny);
         const int gx = remap_index32(p.mode_x, x0 - HL + c, p.nx);
         if (pz < 0 || gy < 0 || gx < 0) return 0.f;
         return __ldg(p.in + (size_t)pz * plane_elems + (size_t)gy * p.nx + gx);
     };
-    auto patch = [&](int batch, int planes) {
-        if (patch_rows) {            // whole rows: float4 copies of the in-range column groups
-            const int nr = oob_top + oob_bot;
-            const int g0 = oob_left / 4, ng = NCG - (oob_left + oob_right) / 4;
-            for (int i = tid; i < planes * nr * ng; i += NT) {
-                const int q = i / (nr * ng), rem = i - q * (nr * ng);
-                const int ra = rem / ng, g = g0 + rem - ra * ng;
-                const int yy = ra < oob_top ? ra : p.box_rows - oob_bot + (ra - oob_top);
-                float* slot = raw + (size_t)q * RSLOT;
-                const int sy = ysrc[yy];
-                float4 v;
-                if (sy >= 0) {
-                    v = *reinterpret_cast<const float4*>(slot + sy * PITCH + 4 * g);
-                } else {
-                    v.x = global_cell(batch, q, yy, 4 * g);     v.y = global_cell(batch, q, yy, 4 * g + 1);
-                    v.z = global_cell(batch, q, yy, 4 * g + 2); v.w = global_cell(batch, q, yy, 4 * g + 3);
+    auto patch = [&](int g) {
+        const int planes = min(G, n_planes - g * G);
+        float* base = raw + (g & 1) * G * RSLOT;
+#pragma unroll
+        for (int sweep = 0; sweep < 2; ++sweep) {
+            const int mr = meta[(2 + sweep) * NT + tid];
+            if (mr != NONE) {
+                const int dst = mr & 0xffff, src = (mr >> 16) & 0xffff;
+                for (int gq = rg0 + (tid & 31); gq < rg1; gq += 32) {
+#pragma unroll
+                    for (int q = 0; q < G; ++q) {
+                        if (q >= planes) break;
+                        float* slot = base + q * RSLOT;
+                        float4 v;
+                        if (src != 0xffff) {
+                            v = *reinterpret_cast<const float4*>(slot + src + 4 * gq);
+                        } else {
+                            v.x = global_cell(g, q, dst + 4 * gq);     v.y = global_cell(g, q, dst + 4 * gq + 1);
+                            v.z = global_cell(g, q, dst + 4 * gq + 2); v.w = global_cell(g, q, dst + 4 * gq + 3);
+                        }
+                        *reinterpret_cast<float4*>(slot + dst + 4 * gq) = v;
+                    }
                 }
-                *reinterpret_cast<float4*>(slot + yy * PITCH + 4 * g) = v;
             }
-        }
-        if (patch_cols) {            // out-of-array columns of every staged row
-            const int nc = oob_left + oob_right;
-            for (int i = tid; i < planes * p.box_rows * nc; i += NT) {
-                const int q = i / (p.box_rows * nc), rem = i - q * (p.box_rows * nc);
-                const int yy = rem / nc, cb = rem - yy * nc;
-                const int c = cb < oob_left ? cb : PITCH - oob_right + (cb - oob_left);
-                const bool row_oob = yy < oob_top || yy >= p.box_rows - oob_bot;
-                if (row_oob && p.mode_y == SEPFILT_CONSTANT) continue;        // stays zero
-                float* slot = raw + (size_t)q * RSLOT;
-                const int sy = row_oob ? ysrc[yy] : yy, sx = xsrc[c];
-                slot[yy * PITCH + c] = (sy >= 0 && sx >= 0) ? slot[sy * PITCH + sx] : global_cell(batch, q, yy, c);
+            const int mc = meta[sweep * NT + tid];
+            if (mc != NONE) {
+                const int dst = mc & 0xffff, src = (mc >> 16) & 0xffff;
+#pragma unroll
+                for (int q = 0; q < G; ++q) {
+                    if (q >= planes) break;
+                    float* slot = base + q * RSLOT;
+                    slot[dst] = src != 0xffff ? slot[src] : global_cell(g, q, dst);
+                }
             }
         }
     };
 
-    // per-thread z accumulators: 2R+1 shifting partial sums for 4 adjacent columns
+    // ---- y pass of one group: raw slot -> ybuf slot, 4 columns x RY rows per thread
+    // (the y-pass items live on the LAST warps of the CTA: when ty < 16 those warps own no output
+    //  rows, which evens out the issue load of the four SM sub-partitions)
+    constexpr int Y_TID0 = NT - ((C::ITEMS + 31) / 32) * 32;
+    const int yi = tid - Y_TID0;
+    const int yq = yi / (2 * NCG), yrem = yi - yq * (2 * NCG);
+    const int yhalf = yrem / NCG, ycg = yrem - yhalf * NCG;
+    const bool y_item = yi >= 0 && yi < C::ITEMS && yhalf * RY < ty;
+    auto ypass = [&](int g) {
+        if (!y_item || g * G + yq >= n_planes) return;
+        u64 acc[RY][2];
+#pragma unroll
+        for (int o = 0; o < RY; ++o) acc[o][0] = acc[o][1] = 0ull;
+        const float* src = raw + ((g & 1) * G + yq) * RSLOT + (yhalf * RY) * PITCH + 4 * ycg;
+#pragma unroll
+        for (int j = 0; j < RY + 2 * R; ++j) {
+            const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(src + j * PITCH);
+#pragma unroll
+            for (int o = 0; o < RY; ++o) {
+                const int k = j - o;
+                if (k >= 0 && k <= 2 * R) {
+                    acc[o][0] = fma2s(v.x, p.wy[k], acc[o][0]);
+                    acc[o][1] = fma2s(v.y, p.wy[k], acc[o][1]);
+                }
+            }
+        }
+        float* dst = ybuf + ((g & 1) * G + yq) * YSLOT + (yhalf * RY) * PITCH + 4 * ycg;
+#pragma unroll
+        for (int o = 0; o < RY; ++o)
+            *reinterpret_cast<ulonglong2*>(dst + o * PITCH) = make_ulonglong2(acc[o][0], acc[o][1]);
+    };
+
+    // ---- x pass + z scatter of one group, plane by plane; 2R+1 shifting z accumulators per column
     u64 zacc[HAS_Z ? 2 * R + 1 : 1][2];
 #pragma unroll
     for (int j = 0; j < (HAS_Z ? 2 * R + 1 : 1); ++j) zacc[j][0] = zacc[j][1] = 0ull;
-
-    const int cg_o = tid & 31, row_o = tid >> 5;          // x+z phase ownership
+    const int cg_o = tid % CGW, row_o = tid / CGW;
     const bool owner = row_o < ty && x0 + 4 * cg_o < p.nx;
     float* out_col = p.out + (size_t)(y0 + row_o) * p.nx + x0 + 4 * cg_o;
+    auto xzpass = [&](int g) {
+        if (!owner) return;
+        const int planes = min(G, n_planes - g * G);
+#pragma unroll
+        for (int q = 0; q < G; ++q) {
+            if (q >= planes) break;
+            const float* src = ybuf + ((g & 1) * G + q) * YSLOT + row_o * PITCH + 4 * cg_o;
+            float win[4 * NV];
+#pragma unroll
+            for (int i = 0; i < NV; ++i) {
+                const float4 v = *reinterpret_cast<const float4*>(src + 4 * i);
+                win[4 * i] = v.x; win[4 * i + 1] = v.y; win[4 * i + 2] = v.z; win[4 * i + 3] = v.w;
+            }
+            float xo[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int k = 0; k <= 2 * R; ++k) {
+                const float w = p.wx[k];
+#pragma unroll
+                for (int o = 0; o < 4; ++o) xo[o] = fmaf(w, win[o + HL - R + k], xo[o]);
+            }
+            const int idx = g * G + q;                     // plane index within this CTA's march
+            if (HAS_Z) {
+                const u64 v0 = pack2(xo[0], xo[1]), v1 = pack2(xo[2], xo[3]);
+#pragma unroll
+                for (int j = 0; j < 2 * R; ++j) {
+                    zacc[j][0] = fma2s(v0, p.wz[2 * R - j], zacc[j + 1][0]);
+                    zacc[j][1] = fma2s(v1, p.wz[2 * R - j], zacc[j + 1][1]);
+                }
+                zacc[2 * R][0] = mul2s(v0, p.wz[0]);
+                zacc[2 * R][1] = mul2s(v1, p.wz[0]);
+                const int zo = zb + idx - 2 * R;           // finished output plane
+                if (zo >= zb)
+                    *reinterpret_cast<ulonglong2*>(out_col + (size_t)zo * plane_elems) =
+                        make_ulonglong2(zacc[0][0], zacc[0][1]);
+            } else {
+                *reinterpret_cast<float4*>(out_col + (size_t)(zb + idx) * plane_elems) =
+                    make_float4(xo[0], xo[1], xo[2], xo[3]);
+            }
+        }
+    };
 
-    if (tid == 0) mbar_init(&full_bar, 1);
+    // ---- software pipeline over groups: raw and ybuf are double buffered, ONE CTA barrier per group.
+    //   phase k:  y pass (k+1) | x+z pass (k) | wait + patch raw (k+2) | barrier | issue TMA (k+3)
+    // (A dataflow variant with per-stage mbarriers instead of the CTA barrier measured slower on
+    //  B200: with two slots per stage every warp still meets every other warp once per group.)
+    auto wait_and_patch = [&](int g) {
+        mbar_wait(&rfull[g & 1], (uint32_t)(g >> 1) & 1u);
+        if (patching) patch(g);
+    };
+    if (tid == 0) { mbar_init(&rfull[0], 1); mbar_init(&rfull[1], 1); }
+    __syncthreads();                                       // barriers + patch metadata visible
+    if (tid == 0) { issue(0); if (n_groups > 1) issue(1); }
+    wait_and_patch(0);
     __syncthreads();
-    if (tid == 0) stage(0);
-    uint32_t parity = 0;
-    for (int batch = 0; batch < n_batches; ++batch) {
-        const int planes = min(PZ, n_planes - batch * PZ);
-        mbar_wait(&full_bar, parity);
-        parity ^= 1;
-        if (patch_rows || patch_cols) patch(batch, planes);
-        __syncthreads();          // patches visible; everyone is done reading ybuf of the previous batch
-
-        // ---- y pass: raw -> ybuf, 4 columns x RY rows per thread
-        {
-            const int q = tid / (2 * NCG);
-            const int rem = tid - q * (2 * NCG);
-            const int half = rem / NCG, cg = rem - half * NCG;
-            if (q < planes && half * RY < ty) {
-                u64 acc[RY][2];
-#pragma unroll
-                for (int o = 0; o < RY; ++o) acc[o][0] = acc[o][1] = 0ull;
-                const float* src = raw + (size_t)q * RSLOT + (half * RY) * PITCH + 4 * cg;
-#pragma unroll
-                for (int j = 0; j < RY + 2 * R; ++j) {
-                    const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(src + j * PITCH);
-#pragma unroll
-                    for (int o = 0; o < RY; ++o) {
-                        const int k = j - o;
-                        if (k >= 0 && k <= 2 * R) {
-                            acc[o][0] = fma2s(v.x, p.wy[k], acc[o][0]);
-                            acc[o][1] = fma2s(v.y, p.wy[k], acc[o][1]);
-                        }
-                    }
-                }
-                float* dst = ybuf + ((size_t)q * TYM + half * RY) * PITCH + 4 * cg;
-#pragma unroll
-                for (int o = 0; o < RY; ++o)
-                    *reinterpret_cast<ulonglong2*>(dst + o * PITCH) = make_ulonglong2(acc[o][0], acc[o][1]);
-            }
-        }
+    ypass(0);
+    if (n_groups > 1) wait_and_patch(1);
+    __syncthreads();
+    if (tid == 0 && n_groups > 2) { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); issue(2); }
+    for (int k = 0; k < n_groups; ++k) {
+        if (k + 1 < n_groups) ypass(k + 1);
+        xzpass(k);
+        if (k + 2 < n_groups) wait_and_patch(k + 2);
         __syncthreads();
-        if (tid == 0 && batch + 1 < n_batches) {           // raw is free: next batch overlaps the x + z phase
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            stage(batch + 1);
-        }
-
-        // ---- x pass + z scatter, plane by plane
-        if (owner) {
-            for (int q = 0; q < planes; ++q) {
-                const float* src = ybuf + ((size_t)q * TYM + row_o) * PITCH + 4 * cg_o;
-                float win[4 * NV];
-#pragma unroll
-                for (int i = 0; i < NV; ++i) {
-                    const float4 v = *reinterpret_cast<const float4*>(src + 4 * i);
-                    win[4 * i] = v.x; win[4 * i + 1] = v.y; win[4 * i + 2] = v.z; win[4 * i + 3] = v.w;
-                }
-                float xo[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-                for (int k = 0; k <= 2 * R; ++k) {
-                    const float w = p.wx[k];
-#pragma unroll
-                    for (int o = 0; o < 4; ++o) xo[o] = fmaf(w, win[o + HL - R + k], xo[o]);
-                }
-                const int idx = batch * PZ + q;            // plane index within this CTA's march
-                if (HAS_Z) {
-                    const u64 v0 = pack2(xo[0], xo[1]), v1 = pack2(xo[2], xo[3]);
-#pragma unroll
-                    for (int j = 0; j < 2 * R; ++j) {
-                        zacc[j][0] = fma2s(v0, p.wz[2 * R - j], zacc[j + 1][0]);
-                        zacc[j][1] = fma2s(v1, p.wz[2 * R - j], zacc[j + 1][1]);
-                    }
-                    zacc[2 * R][0] = mul2s(v0, p.wz[0]);
-                    zacc[2 * R][1] = mul2s(v1, p.wz[0]);
-                    const int zo = zb + idx - 2 * R;       // finished output plane
-                    if (zo >= zb)
-                        *reinterpret_cast<ulonglong2*>(out_col + (size_t)zo * plane_elems) =
-                            make_ulonglong2(zacc[0][0], zacc[0][1]);
-                } else {
-                    *reinterpret_cast<float4*>(out_col + (size_t)(zb + idx) * plane_elems) =
-                        make_float4(xo[0], xo[1], xo[2], xo[3]);
-                }
-            }
-        }
+        if (tid == 0 && k + 3 < n_groups) { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); issue(k + 3); }
     }
+#ifdef SEPFILT_DEBUG_CYCLES
+    if (tid == 0 && blockIdx.x < 4096) g_dbg_cycles[blockIdx.x] = clock64() - t_start;
+#endif
 }
 
 int radius_bucket(int r)
@@ -336,11 +401,9 @@ EncodeTiledFn encode_tiled()
     return fn;
 }
 
-template <int R, bool HAS_Z>
-cudaError_t launch_t(FusedParams& p, cudaStream_t s)
+template <int R, bool HAS_Z, class C>
+cudaError_t launch_c(FusedParams& p, cudaStream_t s)
 {
-    using C = Cfg<R>;
-    static_assert(C::PZ >= 1, "tile too wide");
     p.box_rows = p.ty + 2 * R;
     EncodeTiledFn enc = encode_tiled();
     if (!enc) return cudaErrorNotSupported;
@@ -353,11 +416,11 @@ cudaError_t launch_t(FusedParams& p, cudaStream_t s)
             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
         return cudaErrorInvalidValue;
-    auto kern = fused3d_kernel<R, HAS_Z>;
+    auto kern = fused3d_kernel<R, HAS_Z, C>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
     if (e != cudaSuccess) return e;
     const long long blocks = (long long)p.tiles_x * p.tiles_y * p.nzseg;
-    kern<<<(unsigned)blocks, NT, C::SMEM, s>>>(p, tmap);
+    kern<<<(unsigned)blocks, C::NT, C::SMEM, s>>>(p, tmap);
     return cudaGetLastError();
 }
 
@@ -373,16 +436,73 @@ bool fused3d_supported(const FusedVolume& v, const F32Taps taps[3], bool gradmag
         return false;
     if (v.nx < 1 || v.ny < 1 || v.nz_in < 1 || v.nz_out < 1) return false;
     const bool has_z = !(taps[0].radius == 0 && taps[0].w[0] == 1.0f);
-    if (!has_z && v.nz_out < 4) return false;   // a lone 2-D image cannot fill a plane batch: per-axis passes
+    if (!has_z && v.nz_out < 4) return false;   // a lone 2-D image cannot fill a plane group: per-axis passes
     // constant mode with cval != 0 is affine, not linear: the passes no longer commute and the
     // halo of an intermediate is cval, not filtered cval -> per-axis passes in scipy's order
     if (v.cval != 0.f)
         for (int a = 0; a < 3; ++a)
             if (v.mode[a] == SEPFILT_CONSTANT && taps[a].radius > 0) return false;
-    const long long tiles = (long long)((v.nx + TX - 1) / TX) * v.ny;
+    const long long tiles = (long long)((v.nx + 63) / 64) * v.ny;
     if (tiles * v.nz_out > 2147483647LL) return false;
     return true;
 }
+
+namespace {
+
+// tile rows / z segments for a tile width: fill the SMs with whole waves where the shape allows.
+// Returns the modelled cost (arbitrary units) so that the caller can compare tile widths.
+double plan_tiles(const FusedVolume& v, int R, bool has_z, int tx, int slots, FusedParams* p)
+{
+    const int tiles_x = (v.nx + tx - 1) / tx;
+    int best_ty = TYM, best_seg = 1;
+    double best_cost = 1e300;
+    for (int ty = TYM; ty >= 8; --ty) {
+        const int tiles_y = (v.ny + ty - 1) / ty;
+        for (int nseg = 1; nseg <= 64 && nseg <= v.nz_out; ++nseg) {
+            const int zseg = (v.nz_out + nseg - 1) / nseg;
+            const long long ctas = (long long)tiles_x * tiles_y * nseg;
+            const long long waves = (ctas + slots - 1) / slots;
+            // per-CTA time ~ planes marched x (y pass on a full 16-row tile incl. the x halo + x/z on ty rows)
+            const double per_cta = (double)(zseg + (has_z ? 2 * R : 0)) *
+                                   (0.33 * TYM * (tx + 2 * R) + 0.67 * ty * tx);
+            const double cost = waves * per_cta;
+            if (cost < best_cost) { best_cost = cost; best_ty = ty; best_seg = nseg; }
+            if (!has_z) break;
+        }
+    }
+    if (v.ny <= TYM) best_ty = v.ny < 1 ? 1 : (v.ny < TYM ? v.ny : TYM);
+    if (p) {
+        p->tiles_x = tiles_x;
+        p->ty = best_ty;
+        p->tiles_y = (v.ny + best_ty - 1) / best_ty;
+        p->zseg = (v.nz_out + best_seg - 1) / best_seg;
+        p->nzseg = (v.nz_out + p->zseg - 1) / p->zseg;
+    }
+    return best_cost;
+}
+
+template <int R, bool HAS_Z>
+cudaError_t launch_r(const FusedVolume& v, FusedParams& p, cudaStream_t s)
+{
+    using Wide = Cfg<R, 128, 4, 1>;      // 512 threads, one CTA per SM
+    using Narrow = Cfg<R, 64, 3, 2>;     // 256 threads, two CTAs per SM: one CTA's barrier waits hide behind the other
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    static const char* force = getenv("SEPFILT_FUSED_TILE");
+    const double cw = plan_tiles(v, R, HAS_Z, 128, sms, nullptr);
+    const double cn = plan_tiles(v, R, HAS_Z, 64, 2 * sms, nullptr) * 2.0;   // two CTAs share an SM
+    bool narrow = cn < cw;
+    if (force) narrow = force[0] == 'n';
+    if (narrow) {
+        plan_tiles(v, R, HAS_Z, 64, 2 * sms, &p);
+        return launch_c<R, HAS_Z, Narrow>(p, s);
+    }
+    plan_tiles(v, R, HAS_Z, 128, sms, &p);
+    return launch_c<R, HAS_Z, Wide>(p, s);
+}
+
+}  // namespace
 
 cudaError_t launch_fused3d(const FusedVolume& v, const F32Taps taps[3], const F32Taps[3], bool gradmag,
                            cudaStream_t s)
@@ -403,44 +523,24 @@ cudaError_t launch_fused3d(const FusedVolume& v, const F32Taps taps[3], const F3
     recentre(taps[1], R, p.wy);
     recentre(taps[2], R, p.wx);
 
-    // tile rows / z segments: fill the 148 SMs with whole waves where the shape allows
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    p.tiles_x = (v.nx + TX - 1) / TX;
-    int best_ty = TYM, best_seg = 1;
-    double best_cost = 1e300;
-    for (int ty = TYM; ty >= 8; --ty) {
-        const int tiles_y = (v.ny + ty - 1) / ty;
-        for (int nseg = 1; nseg <= 64 && nseg <= v.nz_out; ++nseg) {
-            const int zseg = (v.nz_out + nseg - 1) / nseg;
-            const long long ctas = (long long)p.tiles_x * tiles_y * nseg;
-            const long long waves = (ctas + sms - 1) / sms;
-            // per-CTA time ~ planes marched x (y-pass on a full 16-row tile + x/z on ty rows)
-            const double per_cta = (double)(zseg + (has_z ? 2 * R : 0)) * (0.36 * TYM + 0.64 * ty);
-            const double cost = waves * per_cta;
-            if (cost < best_cost) { best_cost = cost; best_ty = ty; best_seg = nseg; }
-            if (!has_z) break;
-        }
-    }
-    if (v.ny <= TYM) best_ty = v.ny < 1 ? 1 : (v.ny < TYM ? v.ny : TYM);
-    p.ty = best_ty;
-    p.tiles_y = (v.ny + p.ty - 1) / p.ty;
-    p.nzseg = best_seg;
-    p.zseg = (v.nz_out + best_seg - 1) / best_seg;
-    p.nzseg = (v.nz_out + p.zseg - 1) / p.zseg;
-
     switch (R * 2 + (has_z ? 1 : 0)) {
-    case 1 * 2 + 0: return launch_t<1, false>(p, s);
-    case 1 * 2 + 1: return launch_t<1, true>(p, s);
-    case 2 * 2 + 0: return launch_t<2, false>(p, s);
-    case 2 * 2 + 1: return launch_t<2, true>(p, s);
-    case 4 * 2 + 0: return launch_t<4, false>(p, s);
-    case 4 * 2 + 1: return launch_t<4, true>(p, s);
-    case 8 * 2 + 0: return launch_t<8, false>(p, s);
-    case 8 * 2 + 1: return launch_t<8, true>(p, s);
+    case 1 * 2 + 0: return launch_r<1, false>(v, p, s);
+    case 1 * 2 + 1: return launch_r<1, true>(v, p, s);
+    case 2 * 2 + 0: return launch_r<2, false>(v, p, s);
+    case 2 * 2 + 1: return launch_r<2, true>(v, p, s);
+    case 4 * 2 + 0: return launch_r<4, false>(v, p, s);
+    case 4 * 2 + 1: return launch_r<4, true>(v, p, s);
+    case 8 * 2 + 0: return launch_r<8, false>(v, p, s);
+    case 8 * 2 + 1: return launch_r<8, true>(v, p, s);
     default: return cudaErrorInvalidValue;
     }
 }
 
 }  // namespace sepfilt
+
+#ifdef SEPFILT_DEBUG_CYCLES
+extern "C" __attribute__((visibility("default"))) int sepfilt_debug_cycles(long long* host, int n)
+{
+    return (int)cudaMemcpyFromSymbol(host, sepfilt::g_dbg_cycles, sizeof(long long) * n);
+}
+#endif
