@@ -29,6 +29,16 @@ METRIC = "gaussian_filter 512^3 f32 throughput"
 UNIT = "Gvoxel/s"
 
 
+def _ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the fused kernel on this exact
+    workload, from the committed `ncu --set full` capture (profiles/fused_traffic.json)."""
+    path = os.path.join(ROOT, "profiles", "fused_traffic.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f)
+    return None
+
+
 def _peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -121,7 +131,7 @@ def run_reference(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    sample_planes = 64
+    sample_planes = 256 if cores >= 8 else 64
     cpu_baseline(16, cores)                       # page in, build
     for _ in range(max(args.warmup - 1, 0)):
         cpu_baseline(sample_planes, cores)
@@ -132,8 +142,8 @@ def run_reference(args):
         t_all += t
         vox += sample_planes * NY * NX
     value = vox / t_all / 1e9
-    sample = "%d x %d x %d z-slab of the 512^3 volume per step (1/%d of the workload)" % (
-        sample_planes, NY, NX, NZ // sample_planes)
+    sample = "%d x %d x %d z-slab of the 512^3 volume per step (1/%d of the workload), oracle port on %d threads" % (
+        sample_planes, NY, NX, NZ // sample_planes, cores)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_all / args.steps,
@@ -222,9 +232,10 @@ def run_ours(args):
         b.record()
         b.synchronize()
         kt.append(a.elapsed_time(b))
-    single_launch = (launches // max(world, 1)) == args.steps or world > 1
     kernel_ms = statistics.mean(kt)
-    per_call_launches = max(1, round(launches / max(world, 1) / args.steps)) if world == 1 else None
+    _ffi.LAUNCHES = 0
+    ndi.gaussian_filter(x, SIGMA, output=out, mode=MODE, truncate=TRUNCATE)
+    per_call_launches = _ffi.LAUNCHES            # 1 = fused kernel, 3 = per-axis tiled passes
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- end to end: pinned host -> device -> filter -> host, every step ----
@@ -261,8 +272,10 @@ def run_ours(args):
         # one API call = the algorithmic bytes; with the fused kernel it is one launch, otherwise
         # the per-axis launches share the call and the slowest of them is reported below
         achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
+        tr = _ncu_traffic() if per_call_launches == 1 else None
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": achieved / peak, "traffic": None,
+                    "frac": achieved / peak, "traffic": tr["dram_bytes_per_launch"] if tr else None,
+                    "traffic_source": tr["source"] if tr else None,
                     "kernel": "fused3d_f32 (1 launch per call)" if per_call_launches == 1 else
                               "gaussian_filter call = %s launches (per-axis tiled passes)" % per_call_launches,
                     "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": alg_bytes,
@@ -284,9 +297,13 @@ def run_ours(args):
         }
         if world == 1 and not args.no_cpu:
             cores = os.cpu_count() or 1
-            v, t = cpu_baseline(64, cores)
+            planes = 512 if cores >= 8 else 128
+            cpu_baseline(16, cores)
+            v, t = cpu_baseline(planes, cores)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                                    "sample": "64 x 512 x 512 z-slab (1/8 of the workload), %.1f s" % t}
+                                    "sample": "%d x 512 x 512 z-slab (%s of the workload), oracle port (scipy.ndimage "
+                                              "arithmetic) on %d threads, %.1f s wall" % (
+                                                  planes, "all" if planes == 512 else "1/4", cores, t)}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -62,8 +62,9 @@ template <int R, int TX_, int G_, int CTAS_> struct Cfg {
     static constexpr int RSLOT = (RROWS * PITCH + 31) & ~31;   // floats per raw plane slot (128 B multiple: TMA dst)
     static constexpr int YSLOT = TYM * PITCH;          // floats per y-filtered plane
     static constexpr int ITEMS = 2 * NCG * G;          // y-pass items (4 cols x RY rows) per group
-    // raw[2][G][RSLOT] + ybuf[2][G][YSLOT] + patch metadata[4][NT] + 2 mbarriers
-    static constexpr size_t SMEM = sizeof(float) * (2 * (size_t)G * (RSLOT + YSLOT)) + sizeof(int) * 4 * NT + 16;
+    static constexpr int MAXCELL = RROWS * 2 * HL;     // out-of-array column cells of one plane slot
+    // raw[2][G][RSLOT] + ybuf[2][G][YSLOT] + patch tables (cells + rows) + 3 mbarriers
+    static constexpr size_t SMEM = sizeof(float) * (2 * (size_t)G * (RSLOT + YSLOT)) + sizeof(int) * ((MAXCELL + RROWS + 1) & ~1) + 24;
     static_assert(ITEMS <= NT, "one y-pass item per thread");
 };
 
@@ -102,6 +103,10 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
 {
     asm volatile(
@@ -121,6 +126,18 @@ __device__ __forceinline__ void tma_load_plane(void* dst, const CUtensorMap* map
         : "memory");
 }
 
+// Cold path of the edge patch: a staged cell whose remapped source is not inside the tile (wrap, or
+// arrays smaller than the halo).  Deliberately NOT inlined: inlined, its three modulo remaps were
+// if-converted into the hot patch loop and cost ~4000 cycles per group in every edge tile.
+__device__ __noinline__ float fetch_remapped_cell(const FusedParams& p, int pz, int gy, int gx)
+{
+    pz = remap_index32(p.mode_z, pz, p.nz_in);
+    gy = remap_index32(p.mode_y, gy, p.ny);
+    gx = remap_index32(p.mode_x, gx, p.nx);
+    if (pz < 0 || gy < 0 || gx < 0) return 0.f;
+    return __ldg(p.in + ((size_t)pz * p.ny + gy) * p.nx + gx);
+}
+
 #ifdef SEPFILT_DEBUG_CYCLES
 } __device__ long long g_dbg_cycles[4096]; namespace {
 #endif
@@ -135,12 +152,13 @@ fused3d_kernel(const __grid_constant__ FusedParams p, const __grid_constant__ CU
     extern __shared__ __align__(128) float smem[];
     float* raw = smem;                                    // [2][G] plane slots, box_rows x PITCH dense in each
     float* ybuf = smem + 2 * G * RSLOT;                   // [2][G][TYM][PITCH]
-    int* meta = reinterpret_cast<int*>(ybuf + 2 * G * YSLOT);          // [4][NT] packed patch cells
-    uint64_t* rfull = reinterpret_cast<uint64_t*>(meta + 4 * NT);      // [2] raw slot landed (TMA complete_tx)
+    int* meta = reinterpret_cast<int*>(ybuf + 2 * G * YSLOT);          // patch tables: [MAXCELL] cells + [RROWS] rows
+    uint64_t* rfull = reinterpret_cast<uint64_t*>(meta + ((C::MAXCELL + C::RROWS + 1) & ~1));   // [2] raw slot landed
 
     const int tid = threadIdx.x;
 #ifdef SEPFILT_DEBUG_CYCLES
     const long long t_start = clock64();
+    if (tid == 0) { g_dbg_cycles[1024 + blockIdx.x] = 0; g_dbg_cycles[2048 + blockIdx.x] = 0; g_dbg_cycles[3072 + blockIdx.x] = 0; }
 #endif
     int b = blockIdx.x;
     const int tile_x = b % p.tiles_x; b /= p.tiles_x;
@@ -168,18 +186,27 @@ fused3d_kernel(const __grid_constant__ FusedParams p, const __grid_constant__ CU
     };
 
     // ---- edge tiles: the cells TMA zero-filled are patched from their remapped sources.
-    // Every thread owns up to two fixed out-of-array column cells and two fixed out-of-array
-    // row segments for the whole march; their (destination, source) offsets inside a plane
-    // slot are packed once into shared memory, so a patch is LDS + STS per plane with
-    // immediate plane offsets.  Source 0xffff = not inside this tile (wrap, arrays smaller than
-    // the halo): fetched from global memory.
+    // The (destination, source) offsets of every out-of-array column cell and row of a plane slot
+    // are tabulated once per CTA.  The patch of group k+2 is executed during phase k by the warps
+    // that have NO y-pass items: they finish their x+z work first and would otherwise idle at the
+    // group barrier, so boundary handling hides in that slack.  Source 0xffff = not inside this tile
+    // (wrap, arrays smaller than the halo): fetched from global memory.
+    // (rows / columns further than the halo beyond the array end are never read by a stored voxel)
     const int oob_top = min(p.box_rows, max(0, R - y0)), oob_bot = min(p.box_rows, max(0, y0 + p.box_rows - R - p.ny));
     const int oob_left = min(PITCH, max(0, HL - x0)), oob_right = min(PITCH, max(0, x0 + TX + HL - p.nx));
+    const int need_bot = min(oob_bot, R), need_right = min(oob_right, HL);
     const bool patch_rows = (oob_top + oob_bot) > 0 && p.mode_y != SEPFILT_CONSTANT;
     const bool patch_cols = (oob_left + oob_right) > 0 && p.mode_x != SEPFILT_CONSTANT;
     const bool patching = patch_rows || patch_cols;
     constexpr int NONE = -1;
+    constexpr int NW = NT / 32, NYW = (C::ITEMS + 31) / 32, NPW = NW - NYW;   // warps: all, y-pass, patch
+    static_assert(NPW >= 1, "no warp left for patching");
     const int rg0 = oob_left / 4, rg1 = NCG - oob_right / 4;           // in-range column groups [rg0, rg1)
+    const int ncols = patch_cols ? oob_left + need_right : 0;          // out-of-array columns per staged row
+    const int ncell = ncols * p.box_rows;                              // column cells per plane (<= C::MAXCELL)
+    const int nrow = patch_rows ? oob_top + need_bot : 0;              // out-of-array rows per plane
+    int* pcell = meta;                                                 // [MAXCELL] dst | src << 16
+    int* prow = meta + C::MAXCELL;                                     // [RROWS]   dst | src << 16 (row offsets)
     if (patching) {
         auto staged_row = [&](int yy) {      // staged row holding the source of row yy; -1 stays zero; -2 not in tile
             const int gy = remap_index32(p.mode_y, y0 - R + yy, p.ny);
@@ -193,70 +220,69 @@ fused3d_kernel(const __grid_constant__ FusedParams p, const __grid_constant__ CU
             const int m = gx - (x0 - HL);
             return (m >= 0 && m < PITCH) ? m : -2;
         };
-        constexpr int LANES = (2 * HL <= 16) ? 16 : 2 * HL;           // lanes per staged row of column cells
-        constexpr int CROWS = NT / LANES;
-        static_assert(TYM + 2 * R <= 2 * CROWS, "column cells are covered in two sweeps");
-        for (int sweep = 0; sweep < 2; ++sweep) {
-            int mc = NONE, mr = NONE;
-            const int cb = tid % LANES, nc = oob_left + oob_right, yy = tid / LANES + sweep * CROWS;
-            if (patch_cols && cb < nc && yy < p.box_rows) {
-                const int c = cb < oob_left ? cb : PITCH - oob_right + (cb - oob_left);
-                const bool row_oob = yy < oob_top || yy >= p.box_rows - oob_bot;
-                const int sy = row_oob ? staged_row(yy) : yy, sx = staged_col(c);
-                if (sy != -1 && sx != -1)
-                    mc = (yy * PITCH + c) | (((sy >= 0 && sx >= 0) ? sy * PITCH + sx : 0xffff) << 16);
-            }
-            const int ra = (tid >> 5) + sweep * (NT / 32);
-            if (patch_rows && ra < oob_top + oob_bot) {
-                const int ry = ra < oob_top ? ra : p.box_rows - oob_bot + (ra - oob_top);
-                const int sy = staged_row(ry);
-                if (sy != -1) mr = (ry * PITCH) | ((sy >= 0 ? sy * PITCH : 0xffff) << 16);
-            }
-            meta[sweep * NT + tid] = mc;
-            meta[(2 + sweep) * NT + tid] = mr;
+        for (int i = tid; i < ncell; i += NT) {
+            const int yy = i / ncols, cb = i - yy * ncols;
+            const int c = cb < oob_left ? cb : PITCH - oob_right + (cb - oob_left);
+            const bool row_oob = yy < oob_top || yy >= p.box_rows - oob_bot;
+            const int sy = row_oob ? staged_row(yy) : yy, sx = staged_col(c);
+            int m = NONE;
+            if (sy != -1 && sx != -1)                    // -1: constant-mode zero stays
+                m = (yy * PITCH + c) | (((sy >= 0 && sx >= 0) ? sy * PITCH + sx : 0xffff) << 16);
+            pcell[i] = m;
+        }
+        for (int i = tid; i < nrow; i += NT) {
+            const int ry = i < oob_top ? i : p.box_rows - oob_bot + (i - oob_top);
+            const int sy = staged_row(ry);
+            prow[i] = sy == -1 ? NONE : ((ry * PITCH) | ((sy >= 0 ? sy * PITCH : 0xffff) << 16));
         }
     }
     auto global_cell = [&](int g, int q, int off) -> float {
         const int yy = off / PITCH, c = off - yy * PITCH;
-        const int pz = remap_index32(p.mode_z, p_first + g * G + q, p.nz_in);
-        const int gy = remap_index32(p.mode_y, y0 - R + yy, p.ny);
-        const int gx = remap_index32(p.mode_x, x0 - HL + c, p.nx);
-        if (pz < 0 || gy < 0 || gx < 0) return 0.f;
-        return __ldg(p.in + (size_t)pz * plane_elems + (size_t)gy * p.nx + gx);
+        return fetch_remapped_cell(p, p_first + g * G + q, y0 - R + yy, x0 - HL + c);
     };
-    auto patch = [&](int g) {
+    const bool patch_warp = (tid >> 5) < NPW;
+    auto patch = [&](int g) {                              // executed by the NPW patch warps only
+        // The patch warps share their SM sub-partition with FMA-saturated warps, so every dependent
+        // instruction costs tens of cycles: all loads of a cell (its G planes) are issued before its
+        // stores, and the cold global path is a separate loop.
         const int planes = min(G, n_planes - g * G);
         float* base = raw + (g & 1) * G * RSLOT;
+        for (int ra = tid >> 5; ra < nrow; ra += NPW) {    // rows: float4 copies of the in-range column groups
+            const int mr = prow[ra];
+            if (mr == NONE) continue;
+            const int dst = mr & 0xffff, src = (mr >> 16) & 0xffff;
+            for (int gq = rg0 + (tid & 31); gq < rg1; gq += 32) {
+                if (src != 0xffff) {
+                    float4 v[G];
 #pragma unroll
-        for (int sweep = 0; sweep < 2; ++sweep) {
-            const int mr = meta[(2 + sweep) * NT + tid];
-            if (mr != NONE) {
-                const int dst = mr & 0xffff, src = (mr >> 16) & 0xffff;
-                for (int gq = rg0 + (tid & 31); gq < rg1; gq += 32) {
+                    for (int q = 0; q < G; ++q)
+                        v[q] = *reinterpret_cast<const float4*>(base + q * RSLOT + src + 4 * gq);
 #pragma unroll
-                    for (int q = 0; q < G; ++q) {
-                        if (q >= planes) break;
-                        float* slot = base + q * RSLOT;
+                    for (int q = 0; q < G; ++q)
+                        if (q < planes) *reinterpret_cast<float4*>(base + q * RSLOT + dst + 4 * gq) = v[q];
+                } else {
+                    for (int q = 0; q < planes; ++q) {
                         float4 v;
-                        if (src != 0xffff) {
-                            v = *reinterpret_cast<const float4*>(slot + src + 4 * gq);
-                        } else {
-                            v.x = global_cell(g, q, dst + 4 * gq);     v.y = global_cell(g, q, dst + 4 * gq + 1);
-                            v.z = global_cell(g, q, dst + 4 * gq + 2); v.w = global_cell(g, q, dst + 4 * gq + 3);
-                        }
-                        *reinterpret_cast<float4*>(slot + dst + 4 * gq) = v;
+                        v.x = global_cell(g, q, dst + 4 * gq);     v.y = global_cell(g, q, dst + 4 * gq + 1);
+                        v.z = global_cell(g, q, dst + 4 * gq + 2); v.w = global_cell(g, q, dst + 4 * gq + 3);
+                        *reinterpret_cast<float4*>(base + q * RSLOT + dst + 4 * gq) = v;
                     }
                 }
             }
-            const int mc = meta[sweep * NT + tid];
-            if (mc != NONE) {
-                const int dst = mc & 0xffff, src = (mc >> 16) & 0xffff;
+        }
+        for (int i = tid; i < ncell; i += NPW * 32) {      // column cells
+            const int mc = pcell[i];
+            if (mc == NONE) continue;
+            const int dst = mc & 0xffff, src = (mc >> 16) & 0xffff;
+            if (src != 0xffff) {
+                float v[G];
 #pragma unroll
-                for (int q = 0; q < G; ++q) {
-                    if (q >= planes) break;
-                    float* slot = base + q * RSLOT;
-                    slot[dst] = src != 0xffff ? slot[src] : global_cell(g, q, dst);
-                }
+                for (int q = 0; q < G; ++q) v[q] = base[q * RSLOT + src];
+#pragma unroll
+                for (int q = 0; q < G; ++q)
+                    if (q < planes) base[q * RSLOT + dst] = v[q];
+            } else {
+                for (int q = 0; q < planes; ++q) base[q * RSLOT + dst] = global_cell(g, q, dst);
             }
         }
     };
@@ -269,7 +295,17 @@ fused3d_kernel(const __grid_constant__ FusedParams p, const __grid_constant__ CU
     const int yq = yi / (2 * NCG), yrem = yi - yq * (2 * NCG);
     const int yhalf = yrem / NCG, ycg = yrem - yhalf * NCG;
     const bool y_item = yi >= 0 && yi < C::ITEMS && yhalf * RY < ty;
+    uint64_t* pdone = rfull + 2;                            // raw slot of this phase patched (edge tiles)
     auto ypass = [&](int g) {
+        if (yi < 0) return;                                // not a y-pass warp
+#ifdef SEPFILT_DEBUG_CYCLES
+        const long long tw0 = clock64();
+#endif
+        if (patching) mbar_wait(pdone, (uint32_t)g & 1u);  // patched (implies landed)
+        else mbar_wait(&rfull[g & 1], (uint32_t)(g >> 1) & 1u);   // TMA landed
+#ifdef SEPFILT_DEBUG_CYCLES
+        if (tid == NT - 1) g_dbg_cycles[1024 + blockIdx.x] += clock64() - tw0;
+#endif
         if (!y_item || g * G + yq >= n_planes) return;
         u64 acc[RY][2];
 #pragma unroll
@@ -342,26 +378,38 @@ fused3d_kernel(const __grid_constant__ FusedParams p, const __grid_constant__ CU
     };
 
     // ---- software pipeline over groups: raw and ybuf are double buffered, ONE CTA barrier per group.
-    //   phase k:  y pass (k+1) | x+z pass (k) | wait + patch raw (k+2) | barrier | issue TMA (k+3)
-    // (A dataflow variant with per-stage mbarriers instead of the CTA barrier measured slower on
-    //  B200: with two slots per stage every warp still meets every other warp once per group.)
-    auto wait_and_patch = [&](int g) {
+    // phase k:  [patch warps: wait TMA (k+1), patch it, signal pdone] | x+z pass (k) | y pass (k+1) |
+    //           barrier | issue TMA (k+3)
+    // The TMA of a group is issued two barriers before its first use, the patch runs on the warps that
+    // have no y-pass items while the others are busy with the x+z pass, and the y pass comes last in
+    // the phase: edge handling and load latency both hide behind arithmetic.
+    auto wait_and_patch = [&](int g) {                      // patch warps, edge tiles only
+        if (!patching || !patch_warp || g >= n_groups) return;
+#ifdef SEPFILT_DEBUG_CYCLES
+        const long long tw0 = clock64();
+#endif
         mbar_wait(&rfull[g & 1], (uint32_t)(g >> 1) & 1u);
-        if (patching) patch(g);
+#ifdef SEPFILT_DEBUG_CYCLES
+        const long long tw1 = clock64();
+#endif
+        patch(g);
+#ifdef SEPFILT_DEBUG_CYCLES
+        if (tid == 0) { g_dbg_cycles[2048 + blockIdx.x] += tw1 - tw0; g_dbg_cycles[3072 + blockIdx.x] += clock64() - tw1; }
+#endif
+        __syncwarp();
+        if ((tid & 31) == 0) mbar_arrive(pdone);
     };
-    if (tid == 0) { mbar_init(&rfull[0], 1); mbar_init(&rfull[1], 1); }
-    __syncthreads();                                       // barriers + patch metadata visible
+    if (tid == 0) { mbar_init(&rfull[0], 1); mbar_init(&rfull[1], 1); mbar_init(pdone, NPW); }
+    __syncthreads();                                       // barriers + patch tables visible
     if (tid == 0) { issue(0); if (n_groups > 1) issue(1); }
     wait_and_patch(0);
-    __syncthreads();
     ypass(0);
-    if (n_groups > 1) wait_and_patch(1);
     __syncthreads();
     if (tid == 0 && n_groups > 2) { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); issue(2); }
     for (int k = 0; k < n_groups; ++k) {
-        if (k + 1 < n_groups) ypass(k + 1);
+        wait_and_patch(k + 1);
         xzpass(k);
-        if (k + 2 < n_groups) wait_and_patch(k + 2);
+        if (k + 1 < n_groups) ypass(k + 1);
         __syncthreads();
         if (tid == 0 && k + 3 < n_groups) { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); issue(k + 3); }
     }
