@@ -184,7 +184,29 @@ int sepfilt_correlate1d(const sepfilt_tensor* in, const sepfilt_tensor* out,
         return SEPFILT_OK;
     }
 
-    // ---- exact path ----
+    // ---- exact path, tiled kernels where the geometry and the taps allow ----
+    if (!pass->uniform && c_contiguous(in) && c_contiguous(out)) {
+        const int sym = probe_symmetry(pass->taps, pass->ntaps);
+        ExactTiledGeom g;
+        g.in = in->ptr;
+        g.out = out->ptr;
+        g.in_dtype = in->dtype;
+        g.out_dtype = out->dtype;
+        g.outer = 1;
+        g.inner = 1;
+        for (int d = 0; d < axis; ++d) g.outer *= in->shape[d];
+        for (int d = axis + 1; d < in->ndim; ++d) g.inner *= in->shape[d];
+        g.n_in = in->shape[axis];
+        g.n_out = out->shape[axis];
+        g.shift = in_offset - pass->origin;
+        if (exact_tiled_supported(g, pass->ntaps, sym)) {
+            cudaError_t e = launch_exact_tiled(g, pass->taps, pass->ntaps, sym, pass->mode, cval, s);
+            if (e != cudaSuccess) return fail_cuda(e, "exact_tiled launch");
+            return SEPFILT_OK;
+        }
+    }
+
+    // ---- exact path, per-element kernel (any strides, any taps) ----
     ExactParams p;
     std::memset(&p, 0, sizeof p);
     p.in = static_cast<const char*>(in->ptr);

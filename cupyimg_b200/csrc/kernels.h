@@ -29,6 +29,18 @@ struct ExactParams {
 cudaError_t launch_exact_corr1d(const ExactParams& p, cudaStream_t s);
 cudaError_t launch_gradmag_step(void* acc, const void* a, int64_t n, int dtype, int op, cudaStream_t s);
 
+// ---- exact path, tiled (exact_tiled.cu): C-contiguous arrays, odd symmetric / anti-symmetric taps ----
+struct ExactTiledGeom {
+    const void* in;
+    void*       out;
+    int32_t     in_dtype, out_dtype;
+    int64_t     outer, n_in, n_out, inner;   // (outer, n, inner) view
+    int64_t     shift;                       // source index of the filter centre = output position + shift
+};
+bool        exact_tiled_supported(const ExactTiledGeom& g, int K, int symmetric);
+cudaError_t launch_exact_tiled(const ExactTiledGeom& g, const double* taps, int K, int symmetric, int mode,
+                               double cval, cudaStream_t s);
+
 // ---- f32 tiled 1-D passes (f32_1d.cu): C-contiguous (outer, n, inner) view ----
 struct F32Taps {
     int32_t radius;                       // R: taps cover offsets -R..R (zero padded)
