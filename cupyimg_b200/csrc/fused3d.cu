@@ -22,6 +22,7 @@
 // group k and the TMA traffic of groups k+2 / k+3 overlap, with one CTA barrier per group.  Tensor cores are
 // deliberately not used: this is a bandwidth / FP32-issue bound stencil.
 #include <cuda.h>
+#include <cstddef>
 #include <cstdlib>
 
 #include "common.cuh"
@@ -45,7 +46,13 @@ struct FusedParams {
     int box_rows;               // ty + 2R: height of the TMA box
     int zseg, nzseg;            // output planes per z segment, number of segments
     float wz[2 * MAXR + 1], wy[2 * MAXR + 1], wx[2 * MAXR + 1];   // taps at offsets -R..R
+    int epilogue;               // 0: out = v   1: out = v*v   2: out += v*v   3: out = sqrt(out + v*v)
 };
+
+// Measured on B200 (nvcc 12.9): with the tap arrays at an offset of 4 (mod 8) in the kernel parameter
+// block ptxas pairs the constant-bank taps with the packed FFMA2 operands without extra moves; at
+// 0 (mod 8) the same source compiles to ~70 more MOV/IMAD per loop body and runs 8 % slower.
+static_assert(offsetof(FusedParams, wz) % 8 == 4, "keep the fused kernel's tap arrays at 4 (mod 8) bytes");
 
 __host__ __device__ constexpr int rup4(int r) { return (r + 3) & ~3; }
 
@@ -126,6 +133,19 @@ __device__ __forceinline__ void tma_load_plane(void* dst, const CUtensorMap* map
         : "memory");
 }
 
+// generic_gradient_magnitude staging in the output dtype (filters.py:1187-1201), fused into the store:
+// 1: out = v*v   2: out += v*v   3: out = sqrt(out + v*v); explicit _rn ops, no FMA contraction, so
+// the float32 roundings are the ones of the reference's separate multiply / add / sqrt kernels.
+__device__ __forceinline__ float4 epilogue(int mode, float4 v, const float4* dst)
+{
+    float4 sq = make_float4(__fmul_rn(v.x, v.x), __fmul_rn(v.y, v.y), __fmul_rn(v.z, v.z), __fmul_rn(v.w, v.w));
+    if (mode == 1) return sq;
+    const float4 old = *dst;
+    sq = make_float4(__fadd_rn(old.x, sq.x), __fadd_rn(old.y, sq.y), __fadd_rn(old.z, sq.z), __fadd_rn(old.w, sq.w));
+    if (mode == 2) return sq;
+    return make_float4(__fsqrt_rn(sq.x), __fsqrt_rn(sq.y), __fsqrt_rn(sq.z), __fsqrt_rn(sq.w));
+}
+
 // Cold path of the edge patch: a staged cell whose remapped source is not inside the tile (wrap, or
 // arrays smaller than the halo).  Deliberately NOT inlined: inlined, its three modulo remaps were
 // if-converted into the hot patch loop and cost ~4000 cycles per group in every edge tile.
@@ -142,7 +162,7 @@ __device__ __noinline__ float fetch_remapped_cell(const FusedParams& p, int pz, 
 } __device__ long long g_dbg_cycles[4096]; namespace {
 #endif
 
-template <int R, bool HAS_Z, class C>
+template <int R, bool HAS_Z, class C, bool EPI>
 __global__ void __launch_bounds__(C::NT, C::CTAS)
 fused3d_kernel(const __grid_constant__ FusedParams p, const __grid_constant__ CUtensorMap tmap)
 {
@@ -367,12 +387,21 @@ fused3d_kernel(const __grid_constant__ FusedParams p, const __grid_constant__ CU
                 zacc[2 * R][0] = mul2s(v0, p.wz[0]);
                 zacc[2 * R][1] = mul2s(v1, p.wz[0]);
                 const int zo = zb + idx - 2 * R;           // finished output plane
-                if (zo >= zb)
-                    *reinterpret_cast<ulonglong2*>(out_col + (size_t)zo * plane_elems) =
-                        make_ulonglong2(zacc[0][0], zacc[0][1]);
+                if (zo >= zb) {
+                    float4* dst = reinterpret_cast<float4*>(out_col + (size_t)zo * plane_elems);
+                    if (!EPI) {
+                        *reinterpret_cast<ulonglong2*>(dst) = make_ulonglong2(zacc[0][0], zacc[0][1]);
+                    } else {
+                        float4 v;
+                        asm("mov.b64 {%0, %1}, %2;" : "=f"(v.x), "=f"(v.y) : "l"(zacc[0][0]));
+                        asm("mov.b64 {%0, %1}, %2;" : "=f"(v.z), "=f"(v.w) : "l"(zacc[0][1]));
+                        *dst = epilogue(p.epilogue, v, dst);
+                    }
+                }
             } else {
-                *reinterpret_cast<float4*>(out_col + (size_t)(zb + idx) * plane_elems) =
-                    make_float4(xo[0], xo[1], xo[2], xo[3]);
+                float4* dst = reinterpret_cast<float4*>(out_col + (size_t)(zb + idx) * plane_elems);
+                const float4 v = make_float4(xo[0], xo[1], xo[2], xo[3]);
+                *dst = EPI ? epilogue(p.epilogue, v, dst) : v;
             }
         }
     };
@@ -420,6 +449,9 @@ fused3d_kernel(const __grid_constant__ FusedParams p, const __grid_constant__ CU
 
 int radius_bucket(int r)
 {
+    // radius 16 (33 taps) is NOT fused: 33 z accumulators x 4 columns force 256-thread CTAs on 64-wide
+    // tiles (1.5x y-pass halo work, 2 warps per sub-partition) and measured 1.25 ms on 512^3 against
+    // 1.02 ms for three tiled passes
     static const int buckets[] = {1, 2, 4, 8};
     for (int b : buckets) if (r <= b) return b;
     return -1;
@@ -449,8 +481,17 @@ EncodeTiledFn encode_tiled()
     return fn;
 }
 
+template <int R, bool HAS_Z, class C, bool EPI>
+cudaError_t launch_e(FusedParams& p, cudaStream_t s);
+
 template <int R, bool HAS_Z, class C>
 cudaError_t launch_c(FusedParams& p, cudaStream_t s)
+{
+    return p.epilogue ? launch_e<R, HAS_Z, C, true>(p, s) : launch_e<R, HAS_Z, C, false>(p, s);
+}
+
+template <int R, bool HAS_Z, class C, bool EPI>
+cudaError_t launch_e(FusedParams& p, cudaStream_t s)
 {
     p.box_rows = p.ty + 2 * R;
     EncodeTiledFn enc = encode_tiled();
@@ -464,7 +505,7 @@ cudaError_t launch_c(FusedParams& p, cudaStream_t s)
             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
         return cudaErrorInvalidValue;
-    auto kern = fused3d_kernel<R, HAS_Z, C>;
+    auto kern = fused3d_kernel<R, HAS_Z, C, EPI>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
     if (e != cudaSuccess) return e;
     const long long blocks = (long long)p.tiles_x * p.tiles_y * p.nzseg;
@@ -476,9 +517,9 @@ cudaError_t launch_c(FusedParams& p, cudaStream_t s)
 
 bool fused3d_supported(const FusedVolume& v, const F32Taps taps[3], bool gradmag)
 {
-    if (gradmag) return false;      // fused gradient-magnitude epilogue: next step
     int r = 0;
     for (int a = 0; a < 3; ++a) r = taps[a].radius > r ? taps[a].radius : r;
+    (void)gradmag;   // gradient magnitude = one launch per axis with the square / sum / sqrt in the store
     if (radius_bucket(r) < 0) return false;
     if (v.nx % 4 != 0 || (reinterpret_cast<uintptr_t>(v.in) & 15) || (reinterpret_cast<uintptr_t>(v.out) & 15))
         return false;
@@ -532,11 +573,12 @@ double plan_tiles(const FusedVolume& v, int R, bool has_z, int tx, int slots, Fu
 template <int R, bool HAS_Z>
 cudaError_t launch_r(const FusedVolume& v, FusedParams& p, cudaStream_t s)
 {
-    using Wide = Cfg<R, 128, 4, 1>;      // 512 threads, one CTA per SM
-    using Narrow = Cfg<R, 64, 3, 2>;     // 256 threads, two CTAs per SM: one CTA's barrier waits hide behind the other
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    {
+    using Wide = Cfg<R, 128, 4, 1>;      // 512 threads, one CTA per SM
+    using Narrow = Cfg<R, 64, 3, 2>;     // 256 threads, two CTAs per SM: one CTA's barrier waits hide behind the other
     static const char* force = getenv("SEPFILT_FUSED_TILE");
     const double cw = plan_tiles(v, R, HAS_Z, 128, sms, nullptr);
     const double cn = plan_tiles(v, R, HAS_Z, 64, 2 * sms, nullptr) * 2.0;   // two CTAs share an SM
@@ -548,14 +590,13 @@ cudaError_t launch_r(const FusedVolume& v, FusedParams& p, cudaStream_t s)
     }
     plan_tiles(v, R, HAS_Z, 128, sms, &p);
     return launch_c<R, HAS_Z, Wide>(p, s);
+    }
 }
 
 }  // namespace
 
-cudaError_t launch_fused3d(const FusedVolume& v, const F32Taps taps[3], const F32Taps[3], bool gradmag,
-                           cudaStream_t s)
+static cudaError_t launch_one(const FusedVolume& v, const F32Taps taps[3], int epilogue_mode, cudaStream_t s)
 {
-    if (gradmag) return cudaErrorNotSupported;
     int r = 0;
     for (int a = 0; a < 3; ++a) r = taps[a].radius > r ? taps[a].radius : r;
     const int R = radius_bucket(r);
@@ -567,6 +608,7 @@ cudaError_t launch_fused3d(const FusedVolume& v, const F32Taps taps[3], const F3
     p.nz_in = v.nz_in; p.nz_out = v.nz_out; p.ny = v.ny; p.nx = v.nx; p.z_offset = v.z_offset;
     p.mode_z = v.mode[0]; p.mode_y = v.mode[1]; p.mode_x = v.mode[2];
     p.cval = v.cval;
+    p.epilogue = epilogue_mode;
     recentre(taps[0], R, p.wz);
     recentre(taps[1], R, p.wy);
     recentre(taps[2], R, p.wx);
@@ -582,6 +624,22 @@ cudaError_t launch_fused3d(const FusedVolume& v, const F32Taps taps[3], const F3
     case 8 * 2 + 1: return launch_r<8, true>(v, p, s);
     default: return cudaErrorInvalidValue;
     }
+}
+
+cudaError_t launch_fused3d(const FusedVolume& v, const F32Taps taps[3], const F32Taps dtaps[3], bool gradmag,
+                           cudaStream_t s)
+{
+    if (!gradmag) return launch_one(v, taps, 0, s);
+    // gradient magnitude: sqrt(sum_a (D_a prod_{b != a} S_b in)^2), one launch per filtered axis
+    const int first = (v.nz_in == 1 && v.nz_out == 1 && taps[0].radius == 0 && dtaps[0].radius == 0) ? 1 : 0;
+    for (int a = first; a < 3; ++a) {
+        F32Taps t[3] = {taps[0], taps[1], taps[2]};
+        t[a] = dtaps[a];
+        const int mode = a == first ? 1 : (a == 2 ? 3 : 2);
+        cudaError_t e = launch_one(v, t, first == 2 ? 3 : mode, s);
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
 }
 
 }  // namespace sepfilt

@@ -297,6 +297,7 @@ def test_f32_filters_match_oracle(mode, ndi):
         xd = to_device(x)
         for name, args, kw in [
             ("gaussian_filter", (2.0,), {}), ("gaussian_filter", (1.0,), {"truncate": 3.0}),
+            ("gaussian_filter", (4.0,), {}), ("gaussian_gradient_magnitude", (3.0,), {}),
             ("gaussian_filter", ([1.5, 0.0, 2.5][:len(shape)],), {}),
             ("gaussian_filter", (1.5,), {"order": ([0, 1, 0][:len(shape)])}),
             ("uniform_filter", (5,), {}), ("uniform_filter", (4,), {"origin": -1}),
