@@ -223,7 +223,8 @@ fused3d_kernel(const __grid_constant__ FusedParams p, const __grid_constant__ CU
     static_assert(NPW >= 1, "no warp left for patching");
     const int rg0 = oob_left / 4, rg1 = NCG - oob_right / 4;           // in-range column groups [rg0, rg1)
     const int ncols = patch_cols ? oob_left + need_right : 0;          // out-of-array columns per staged row
-    const int ncell = ncols * p.box_rows;                              // column cells per plane (<= C::MAXCELL)
+    const int rows_used = p.box_rows - (oob_bot - need_bot);           // staged rows a stored voxel can read
+    const int ncell = ncols * rows_used;                               // column cells per plane (<= C::MAXCELL)
     const int nrow = patch_rows ? oob_top + need_bot : 0;              // out-of-array rows per plane
     int* pcell = meta;                                                 // [MAXCELL] dst | src << 16
     int* prow = meta + C::MAXCELL;                                     // [RROWS]   dst | src << 16 (row offsets)
@@ -559,6 +560,10 @@ double plan_tiles(const FusedVolume& v, int R, bool has_z, int tx, int slots, Fu
             if (!has_z) break;
         }
     }
+    if (const char* fty = getenv("SEPFILT_FUSED_TY")) {          // tuning aid: force the tile height
+        const int t = atoi(fty);
+        if (t >= 1 && t <= TYM) { best_ty = t; best_seg = 1; }
+    }
     if (v.ny <= TYM) best_ty = v.ny < 1 ? 1 : (v.ny < TYM ? v.ny : TYM);
     if (p) {
         p->tiles_x = tiles_x;
@@ -576,6 +581,12 @@ cudaError_t launch_r(const FusedVolume& v, FusedParams& p, cudaStream_t s)
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    // SMs to leave free for a concurrent communication kernel (the sharded path sets this): a
+    // one-wave grid that needs EVERY SM would otherwise serialise behind the SMs NCCL occupies
+    if (const char* rs = getenv("SEPFILT_RESERVE_SMS")) {
+        const int r = atoi(rs);
+        if (r > 0 && r < sms) sms -= r;
+    }
     {
     using Wide = Cfg<R, 128, 4, 1>;      // 512 threads, one CTA per SM
     using Narrow = Cfg<R, 64, 3, 2>;     // 256 threads, two CTAs per SM: one CTA's barrier waits hide behind the other

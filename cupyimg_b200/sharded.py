@@ -12,6 +12,8 @@
 The reference is single-GPU (no collectives anywhere); this is the
 B200 scale-out of its per-axis loops (filters.py:651-662, :777-789).
 """
+import os
+
 import numpy as np
 import torch
 import torch.distributed as dist
@@ -64,6 +66,10 @@ class ZSlabFilter:
         self.hi_ext = torch.empty(shape, dtype=dtype, device=self.device) if self.has_hi and r else None
         self.on_cuda = self.device.type == "cuda"
         self.comm_stream = torch.cuda.Stream(self.device) if self.on_cuda else None
+        if self.world > 1 and self.on_cuda:
+            # the interior launch overlaps the NCCL send/recv kernels: leave them a few SMs, otherwise a
+            # grid sized to fill every SM in one wave waits for the SMs NCCL holds and runs two waves
+            os.environ.setdefault("SEPFILT_RESERVE_SMS", "8")
 
     # -- halo exchange ---------------------------------------------------------------
     def _peer(self, step):

@@ -20,8 +20,10 @@
  *   - running-sum uniform filter (App. C.3),
  *   - C casts for the store (App. C.4).
  * Pinned by tests/test_oracle.py against (i) the literal known-answer tables of the
- * reference test-suite (tests/golden/reference_kats.json), (ii) scipy.ndimage run in
- * the same process, bit-for-bit.
+ * reference test-suite (tests/golden/reference_kats.json), (ii) 2680 outputs of the reference
+ * ITSELF, executed on the CPU from the kernel source its own generator emits
+ * (tests/golden/make_reference_vectors.py -> reference_vectors.npz), (iii) scipy.ndimage run
+ * in the same process, bit-for-bit.
  *
  * Build: gcc -O2 -ffp-contract=off -fPIC -shared (see oracle/Makefile).  -ffp-contract=off
  * matters: scipy's binary does not contract a*b+c into FMA.

@@ -8,7 +8,8 @@ import threading
 import numpy as np
 import pytest
 
-from helpers import TYPES, gpu_call, load_kats, run_kat, to_device, to_host
+from helpers import (TYPES, call_filter, check_against_reference, gpu_call, load_kats, load_reference_vectors,
+                     run_kat, to_device, to_host)
 from oracle import oracle
 
 pytestmark = pytest.mark.gpu
@@ -48,6 +49,29 @@ def _gpu_kat_call(func, x, **kw):
 @pytest.mark.parametrize("case", KATS, ids=[c["id"] for c in KATS])
 def test_reference_known_answers(case, ndi):
     run_kat(case, _gpu_kat_call)
+
+
+def test_reference_executed_vectors(ndi):
+    """The CUDA path (exact kernels, dtype_mode='ndimage') against outputs of the reference itself,
+    executed on the CPU from its own generated kernel source (tests/golden/make_reference_vectors.py)."""
+    class GpuNs:
+        def __getattr__(self, name):
+            fn = getattr(ndi, name)
+            return lambda x, *a, **kw: to_host(fn(to_device(x), *a, dtype_mode="ndimage", **kw))
+    n = {"checked": 0, "skipped": 0}
+    for func, kwargs, x, ref in load_reference_vectors():
+        if func in ("laplace", "gaussian_gradient_magnitude"):       # no dtype_mode keyword on these two
+            kw = dict(kwargs)
+            first = [kw.pop("sigma")] if "sigma" in kw else []
+            got = to_host(getattr(ndi, func)(to_device(x), *first, **kw))
+            if ref.dtype == np.float32:                               # float32 kernels: tolerance, not bits
+                np.testing.assert_allclose(got, ref, rtol=1e-5, atol=2e-6 * float(np.abs(ref).max()))
+                n["checked"] += 1
+                continue
+        else:
+            got = call_filter(GpuNs(), func, x, kwargs)
+        n[check_against_reference(func, x, got, ref)] += 1
+    assert n["checked"] > 1000
 
 
 # ---------------------------------------------------------------- exact path

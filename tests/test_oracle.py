@@ -8,7 +8,7 @@ import pytest
 from scipy import ndimage as sndi
 
 from oracle import oracle
-from helpers import TYPES, load_kats, run_kat
+from helpers import TYPES, call_filter, check_against_reference, load_kats, load_reference_vectors, run_kat
 
 KATS = load_kats()
 
@@ -117,3 +117,13 @@ def test_window_semantics():
     out = np.empty((6, 6, 5), np.float32)
     oracle._line_pass(ext, out, 0, w, w.size, 0, "reflect", 0.0, in_offset=4)
     np.testing.assert_array_equal(out, full[7:13])
+
+
+def test_reference_executed_vectors():
+    """The oracle against outputs of the reference ITSELF, executed on the CPU by compiling the kernel
+    source its own generator emits (tests/golden/make_reference_vectors.py)."""
+    n = {"checked": 0, "skipped": 0}
+    for func, kwargs, x, ref in load_reference_vectors():
+        got = call_filter(oracle, func, x, kwargs)
+        n[check_against_reference(func, x, got, ref)] += 1
+    assert n["checked"] > 1000 and n["skipped"] < 0.02 * n["checked"]
