@@ -26,6 +26,7 @@ Where the reference deviates from scipy this module follows s
 ``uniform_filter`` uses an exact window sum / size, ``convolve1d`` honours ``cval``,
 ``grid-constant`` == ``constant``, Gaussian taps stay float64.
 """
+import functools
 import numbers
 
 import numpy as np
@@ -384,6 +385,15 @@ def uniform_filter(input, size=3, output=None, mode="reflect", cval=0.0, origin=
     return _array.export(out, inp)
 
 
+@functools.lru_cache(maxsize=256)
+def _gaussian_taps_cached(sigma, order, radius):
+    """Correlation-orientation taps (reversed kernel, filters.py:717-718), cached: a scale-space loop
+    or a benchmark calls the same (sigma, order, radius) thousands of times."""
+    taps = _gaussian_kernel1d(sigma, order, radius)[::-1].copy()
+    taps.setflags(write=False)
+    return taps
+
+
 def _gaussian_kernel1d(sigma, order, radius):
     """Taps of a Gaussian (or its ``order``-th derivative), convolution orientation
     (reference filters.py:795-825 == scipy's; float64 throughout)."""
@@ -416,8 +426,7 @@ def _gaussian_spec(axis, sigma, order, mode_code, truncate, radius=None):
         lw = radius
     if not isinstance(lw, numbers.Integral) or lw < 0:
         raise ValueError("Radius must be a nonnegative integer.")
-    # correlation orientation: reversed kernel (filters.py:717-718)
-    return _PassSpec(axis, _gaussian_kernel1d(sd, int(order), int(lw))[::-1].copy(), 0, mode_code)
+    return _PassSpec(axis, _gaussian_taps_cached(sd, int(order), int(lw)), 0, mode_code)
 
 
 def gaussian_filter1d(input, sigma, axis=-1, order=0, output=None, mode="reflect", cval=0.0,
