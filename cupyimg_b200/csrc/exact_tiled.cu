@@ -24,21 +24,41 @@ namespace sepfilt {
 
 namespace {
 
-__device__ __forceinline__ double load_any(const char* base, int dtype, int64_t idx)
+// run f.template operator()<T>() with T = the element type of `dtype`: the switch is taken once per
+// thread, outside the staging / store loops, instead of once per element
+template <class F>
+__device__ __forceinline__ void dispatch_dtype(int dtype, F&& f)
 {
     switch (dtype) {
-    case SEPFILT_I8:  return (double)reinterpret_cast<const int8_t*>(base)[idx];
-    case SEPFILT_U8: case SEPFILT_BOOL: return (double)reinterpret_cast<const uint8_t*>(base)[idx];
-    case SEPFILT_I16: return (double)reinterpret_cast<const int16_t*>(base)[idx];
-    case SEPFILT_U16: return (double)reinterpret_cast<const uint16_t*>(base)[idx];
-    case SEPFILT_I32: return (double)reinterpret_cast<const int32_t*>(base)[idx];
-    case SEPFILT_U32: return (double)reinterpret_cast<const uint32_t*>(base)[idx];
-    case SEPFILT_I64: return (double)reinterpret_cast<const int64_t*>(base)[idx];
-    case SEPFILT_U64: return (double)reinterpret_cast<const uint64_t*>(base)[idx];
-    case SEPFILT_F32: return (double)reinterpret_cast<const float*>(base)[idx];
-    default:          return reinterpret_cast<const double*>(base)[idx];
+    case SEPFILT_I8:  f.template operator()<int8_t>(); break;
+    case SEPFILT_U8: case SEPFILT_BOOL: f.template operator()<uint8_t>(); break;
+    case SEPFILT_I16: f.template operator()<int16_t>(); break;
+    case SEPFILT_U16: f.template operator()<uint16_t>(); break;
+    case SEPFILT_I32: f.template operator()<int32_t>(); break;
+    case SEPFILT_U32: f.template operator()<uint32_t>(); break;
+    case SEPFILT_I64: f.template operator()<int64_t>(); break;
+    case SEPFILT_U64: f.template operator()<uint64_t>(); break;
+    case SEPFILT_F32: f.template operator()<float>(); break;
+    default:          f.template operator()<double>(); break;
     }
 }
+
+// typed store under the same cast rules as store_cast (common.cuh), without the per-element switch
+template <class T> __device__ __forceinline__ T cast_out(double v);
+template <> __device__ __forceinline__ int8_t   cast_out<int8_t>(double v)   { return (int8_t)cvt_x86_i32(v); }
+template <> __device__ __forceinline__ uint8_t  cast_out<uint8_t>(double v)  { return (uint8_t)cvt_x86_i32(v); }
+template <> __device__ __forceinline__ int16_t  cast_out<int16_t>(double v)  { return (int16_t)cvt_x86_i32(v); }
+template <> __device__ __forceinline__ uint16_t cast_out<uint16_t>(double v) { return (uint16_t)cvt_x86_i32(v); }
+template <> __device__ __forceinline__ int32_t  cast_out<int32_t>(double v)  { return cvt_x86_i32(v); }
+template <> __device__ __forceinline__ uint32_t cast_out<uint32_t>(double v) { return (uint32_t)cvt_x86_i64(v); }
+template <> __device__ __forceinline__ int64_t  cast_out<int64_t>(double v)  { return cvt_x86_i64(v); }
+template <> __device__ __forceinline__ uint64_t cast_out<uint64_t>(double v)
+{
+    return (v < 9223372036854775808.0) ? (uint64_t)cvt_x86_i64(v)
+                                       : ((uint64_t)cvt_x86_i64(v - 9223372036854775808.0) ^ 0x8000000000000000ull);
+}
+template <> __device__ __forceinline__ float    cast_out<float>(double v)    { return __double2float_rn(v); }
+template <> __device__ __forceinline__ double   cast_out<double>(double v)   { return v; }
 
 struct SymParams {
     const char* in;
@@ -77,13 +97,19 @@ exact_sym_row_kernel(const __grid_constant__ SymParams p)
     const int x0 = blockIdx.y * XR_W;
     const int tid = threadIdx.x;
     const int src0 = x0 + p.shift - R;
-    for (int i = tid; i < XR_ROWS * PITCH; i += 256) {
-        const int r = i / PITCH, s = i - r * PITCH;
-        const int64_t row = row0 + r;
-        if (row >= p.outer) continue;
-        const int m = remap_index32(p.mode, src0 + s, p.n_in);
-        tile[r][s] = m < 0 ? p.cval : load_any(p.in, p.in_dtype, row * p.n_in + m);
-    }
+    const bool interior = src0 >= 0 && src0 + PITCH <= p.n_in;     // no cell of this tile needs remapping
+    dispatch_dtype(p.in_dtype, [&]<class T>() {
+        const T* in = reinterpret_cast<const T*>(p.in);
+#pragma unroll 2
+        for (int i = tid; i < XR_ROWS * PITCH; i += 256) {
+            const int r = i / PITCH, s = i - r * PITCH;
+            const int64_t row = row0 + r;
+            if (row >= p.outer) continue;
+            int m = src0 + s;
+            if (!interior) m = remap_index32(p.mode, m, p.n_in);
+            tile[r][s] = m < 0 ? p.cval : (double)in[row * p.n_in + m];
+        }
+    });
     __syncthreads();
     const int r = tid >> 6, c = (tid & 63) * 4;
     const int64_t row = row0 + r;
@@ -92,10 +118,15 @@ exact_sym_row_kernel(const __grid_constant__ SymParams p)
     double win[4 + 2 * R];
 #pragma unroll
     for (int i = 0; i < 4 + 2 * R; ++i) win[i] = tile[r][c + i];
-    char* dst = p.out + (row * p.n_out + x) * p.out_size;
+    double res[4];
 #pragma unroll
-    for (int o = 0; o < 4; ++o)
-        if (x + o < p.n_out) store_cast(dst + o * p.out_size, p.out_dtype, sym_acc<R, SGN>(win + o, p));
+    for (int o = 0; o < 4; ++o) res[o] = sym_acc<R, SGN>(win + o, p);
+    dispatch_dtype(p.out_dtype, [&]<class T>() {
+        T* dst = reinterpret_cast<T*>(p.out) + row * p.n_out + x;
+#pragma unroll
+        for (int o = 0; o < 4; ++o)
+            if (x + o < p.n_out) dst[o] = cast_out<T>(res[o]);
+    });
 }
 
 constexpr int XC_TI = 64, XC_RN = 4;
@@ -116,16 +147,17 @@ exact_sym_col_kernel(const __grid_constant__ SymParams p, const int n_itiles)
     const int64_t in_base = o * (int64_t)p.n_in * p.inner;
     const int src0 = n0 + p.shift - R;
     const int rows_needed = min(ROWS, p.n_out - n0 + 2 * R);
-    {
+    dispatch_dtype(p.in_dtype, [&]<class T>() {
         const int lane = tid & 63;
         const int64_t ii = i0 + lane;
+        const T* col = reinterpret_cast<const T*>(p.in) + in_base + ii;
+        const bool inside = ii < p.inner;
+#pragma unroll 4
         for (int e = tid >> 6; e < rows_needed; e += 4) {
             const int m = remap_index32(p.mode, src0 + e, p.n_in);
-            double v = p.cval;
-            if (m >= 0 && ii < p.inner) v = load_any(p.in, p.in_dtype, in_base + (int64_t)m * p.inner + ii);
-            tile[e][lane] = v;
+            tile[e][lane] = (m >= 0 && inside) ? (double)col[(int64_t)m * p.inner] : p.cval;
         }
-    }
+    });
     __syncthreads();
     const int ti = tid & 31, tn = tid >> 5;
     const int64_t ii = i0 + 2 * ti;
@@ -137,14 +169,18 @@ exact_sym_col_kernel(const __grid_constant__ SymParams p, const int n_itiles)
         const double2 v = *reinterpret_cast<const double2*>(&tile[tn * XC_RN + j][2 * ti]);
         wa[j] = v.x; wb[j] = v.y;
     }
+    double ra[XC_RN], rb[XC_RN];
 #pragma unroll
-    for (int q = 0; q < XC_RN; ++q) {
-        const int pp = p0 + q;
-        if (pp >= p.n_out) break;
-        char* dst = p.out + ((o * (int64_t)p.n_out + pp) * p.inner + ii) * p.out_size;
-        store_cast(dst, p.out_dtype, sym_acc<R, SGN>(wa + q, p));
-        if (ii + 1 < p.inner) store_cast(dst + p.out_size, p.out_dtype, sym_acc<R, SGN>(wb + q, p));
-    }
+    for (int q = 0; q < XC_RN; ++q) { ra[q] = sym_acc<R, SGN>(wa + q, p); rb[q] = sym_acc<R, SGN>(wb + q, p); }
+    dispatch_dtype(p.out_dtype, [&]<class T>() {
+        T* dst = reinterpret_cast<T*>(p.out) + (o * (int64_t)p.n_out + p0) * p.inner + ii;
+#pragma unroll
+        for (int q = 0; q < XC_RN; ++q) {
+            if (p0 + q >= p.n_out) break;
+            dst[(int64_t)q * p.inner] = cast_out<T>(ra[q]);
+            if (ii + 1 < p.inner) dst[(int64_t)q * p.inner + 1] = cast_out<T>(rb[q]);
+        }
+    });
 }
 
 int sym_bucket(int r)

@@ -132,7 +132,7 @@ def _host_taps(weights):
 class _PassSpec:
     """One 1-D pass: taps (host float64) or a uniform window, in correlation orientation."""
 
-    __slots__ = ("axis", "taps", "size", "origin", "mode", "uniform")
+    __slots__ = ("axis", "taps", "size", "origin", "mode", "uniform", "_struct")
 
     def __init__(self, axis, taps, origin, mode, uniform=False, size=0):
         self.axis = axis
@@ -141,13 +141,17 @@ class _PassSpec:
         self.origin = int(origin)
         self.mode = mode                # integer mode code
         self.uniform = uniform
+        self._struct = None
 
     def radius(self):
         before = self.size // 2 + self.origin
         return max(before, self.size - 1 - before)
 
     def struct(self):
-        return _ffi.make_pass(self.axis, self.taps, self.origin, self.mode, self.uniform, self.size)
+        """(ctypes Pass, keepalive) — built once per spec."""
+        if self._struct is None:
+            self._struct = _ffi.make_pass(self.axis, self.taps, self.origin, self.mode, self.uniform, self.size)
+        return self._struct
 
 
 def _f32_tiled_ok(src, dst, spec):
@@ -186,34 +190,34 @@ def _copy_cast(src, dst):
     _ffi.count_launch()
 
 
-def _fused_ok(inp, out, specs, exact, cval=0.0, gradmag=False):
+def _fused_candidate(inp, out, specs, exact, gradmag=False):
+    """Cheap host-side screen for the fused float32 kernel; the library has the last word
+    (sepfilt_separable_f32 answers SEPFILT_ERR_UNSUPPORTED and the caller falls back per axis)."""
     if exact or inp.dtype != _F32 or out.dtype != _F32 or inp.ndim not in (2, 3):
         return False
-    if not (inp.c_contiguous() and out.c_contiguous()) or inp.may_overlap(out) or inp.size == 0:
-        return False
-    if any(s.radius() > _ffi.FAST_MAX_RADIUS or s.radius() > inp.shape[s.axis] for s in specs):
+    if not (inp.c_contiguous() and out.c_contiguous()) or inp.size == 0 or inp.may_overlap(out):
         return False
     if len(specs) < 2 and not gradmag:
         return False                    # a single axis is served by the tiled 1-D pass
-    structs = [s.struct() for s in specs]
-    arr = (_ffi.Pass * len(structs))(*[s[0] for s in structs])
-    return bool(_ffi.lib().sepfilt_separable_f32_supported(inp.tensor(), out.tensor(), arr, len(structs),
-                                                           1 if gradmag else 0, float(cval)))
+    return all(s.radius() <= _ffi.FAST_MAX_RADIUS and s.radius() <= inp.shape[s.axis] for s in specs)
 
 
-def _launch_fused(inp, out, specs, cval, dspecs=None, in_offset0=0):
+def _try_fused(inp, out, specs, cval, dspecs=None, in_offset0=0):
+    """One sepfilt_separable_f32 call; False when the library declines the request."""
     structs = [s.struct() for s in specs]
     arr = (_ffi.Pass * len(structs))(*[s[0] for s in structs])
-    darr, dstructs = None, None
+    darr = None
     if dspecs is not None:
         dstructs = [s.struct() for s in dspecs]
         darr = (_ffi.Pass * len(dstructs))(*[s[0] for s in dstructs])
     rc = _ffi.lib().sepfilt_separable_f32(inp.tensor(), out.tensor(), arr, len(structs), darr,
                                           1 if dspecs is not None else 0, int(in_offset0), float(cval),
                                           _array.current_stream(inp.device))
+    if rc == _ffi.ERR_UNSUPPORTED:
+        return False
     _ffi.check(rc)
-    _ffi.count_launch()
-    del structs, dstructs
+    _ffi.count_launch(1 if dspecs is None else len(structs))
+    return True
 
 
 def _run_passes(inp, out, specs, cval, dtype_mode):
@@ -235,8 +239,7 @@ def _run_passes(inp, out, specs, cval, dtype_mode):
         else:
             _copy_cast(inp, out)
         return out
-    if _fused_ok(inp, out, specs, exact, cval):
-        _launch_fused(inp, out, specs, cval)
+    if _fused_candidate(inp, out, specs, exact) and _try_fused(inp, out, specs, cval):
         return out
     n = len(specs)
     aliased = inp.may_overlap(out)
@@ -274,8 +277,7 @@ def _run_passes_window(inp, out, specs, cval, dtype_mode, in_offset0):
     exact = dtype_mode == "ndimage"
     if inp.may_overlap(out):
         raise RuntimeError("windowed filtering cannot run in place")
-    if _fused_ok(inp, out, specs, exact, cval):
-        _launch_fused(inp, out, specs, cval, in_offset0=in_offset0)
+    if _fused_candidate(inp, out, specs, exact) and _try_fused(inp, out, specs, cval, in_offset0=in_offset0):
         return out
     specs = list(specs)
     if not specs or specs[0].axis != 0:
@@ -591,8 +593,8 @@ def gaussian_gradient_magnitude(input, sigma, output=None, mode="reflect", cval=
         if out.dtype == _F32:
             smooth = _gaussian_specs(inp, sigma, 0, mode, truncate)
             deriv = _gaussian_specs(inp, sigma, 1, mode, truncate)
-            if len(smooth) == ndim and _fused_ok(inp, out, smooth, False, cval, gradmag=True):
-                _launch_fused(inp, out, smooth, cval, dspecs=deriv)
+            if len(smooth) == ndim and len(deriv) == ndim and _fused_candidate(inp, out, smooth, False, gradmag=True) \
+                    and _try_fused(inp, out, smooth, cval, dspecs=deriv):
                 return _array.export(out, inp)
         output = out.obj
 
