@@ -33,7 +33,6 @@ namespace sepfilt {
 namespace {
 
 constexpr int TYM = 16;     // max tile rows
-constexpr int RY = 8;       // rows per y-pass register tile
 constexpr int MAXR = SEPFILT_FAST_MAX_RADIUS;
 
 struct FusedParams {
@@ -58,8 +57,9 @@ __host__ __device__ constexpr int rup4(int r) { return (r + 3) & ~3; }
 
 // TX: tile width along the contiguous axis; NT = TX * TYM / 4 threads (one float4 column group x one
 // row each in the x+z pass); G: planes per pipeline group; CTAS: co-resident CTAs per SM.
-template <int R, int TX_, int G_, int CTAS_> struct Cfg {
-    static constexpr int TX = TX_, NT = TX_ * TYM / 4, CTAS = CTAS_;
+// RY: rows per y-pass register tile; a tile of ty <= 2 * RY rows is covered by two row halves.
+template <int R, int TX_, int G_, int CTAS_, int RY_ = 8> struct Cfg {
+    static constexpr int TX = TX_, NT = TX_ * TYM / 4, CTAS = CTAS_, RY = RY_;
     static constexpr int HL = rup4(R);                 // x halo staged (multiple of 4 floats)
     static constexpr int PITCH = TX + 2 * HL;          // floats per staged row
     static constexpr int NCG = PITCH / 4;              // float4 column groups per row
@@ -166,7 +166,7 @@ template <int R, bool HAS_Z, class C, bool EPI>
 __global__ void __launch_bounds__(C::NT, C::CTAS)
 fused3d_kernel(const __grid_constant__ FusedParams p, const __grid_constant__ CUtensorMap tmap)
 {
-    constexpr int TX = C::TX, NT = C::NT, CGW = TX / 4;
+    constexpr int TX = C::TX, NT = C::NT, CGW = TX / 4, RY = C::RY;
     constexpr int HL = C::HL, PITCH = C::PITCH, NCG = C::NCG, G = C::G, NV = C::NV;
     constexpr int RSLOT = C::RSLOT, YSLOT = C::YSLOT;
     extern __shared__ __align__(128) float smem[];
@@ -600,6 +600,9 @@ cudaError_t launch_r(const FusedVolume& v, FusedParams& p, cudaStream_t s)
         return launch_c<R, HAS_Z, Narrow>(p, s);
     }
     plan_tiles(v, R, HAS_Z, 128, sms, &p);
+    // tiles of <= 14 rows (e.g. 512 rows = 37 x 14 on 148 SMs): 7-row y-pass register tiles, so that the
+    // y pass does not filter two rows per tile that nobody reads
+    if (p.ty <= 14 && p.ty > 8) return launch_c<R, HAS_Z, Cfg<R, 128, 4, 1, 7>>(p, s);
     return launch_c<R, HAS_Z, Wide>(p, s);
     }
 }
