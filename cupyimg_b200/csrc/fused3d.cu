@@ -71,7 +71,7 @@ template <int R, int TX_, int G_, int CTAS_, int RY_ = 8> struct Cfg {
     static constexpr int ITEMS = 2 * NCG * G;          // y-pass items (4 cols x RY rows) per group
     static constexpr int MAXCELL = RROWS * 2 * HL;     // out-of-array column cells of one plane slot
     // raw[2][G][RSLOT] + ybuf[2][G][YSLOT] + patch tables (cells + rows) + 3 mbarriers + patch parameters
-    static constexpr size_t SMEM = sizeof(float) * (2 * (size_t)G * (RSLOT + YSLOT)) + sizeof(int) * ((MAXCELL + RROWS + 1) & ~1) + 48;
+    static constexpr size_t SMEM = sizeof(float) * (2 * (size_t)G * (RSLOT + YSLOT)) + sizeof(int) * ((MAXCELL + RROWS + 1) & ~1) + 80;
     static_assert(ITEMS <= NT, "one y-pass item per thread");
 };
 
@@ -194,14 +194,17 @@ fused3d_kernel(const __grid_constant__ FusedParams p, const __grid_constant__ CU
     const size_t plane_elems = (size_t)p.ny * p.nx;
 
     // ---- stage one group: one TMA box per plane into raw slot (g & 1), issued by a single thread
-    auto issue = [&](int g) {
-        const int planes = min(G, n_planes - g * G);
+    int* iinfo = reinterpret_cast<int*>(rfull + 4) + 8;    // the issuing thread's coordinates, kept out of registers
+    if (tid == 0) { iinfo[0] = x0 - HL; iinfo[1] = y0 - R; iinfo[2] = p_first; iinfo[3] = n_planes; }
+    auto issue = [&](int g) {                               // thread 0 only
+        const int cx = iinfo[0], cy = iinfo[1], first = iinfo[2];
+        const int planes = min(G, iinfo[3] - g * G);
         uint64_t* bar = &rfull[g & 1];
         mbar_expect_tx(bar, (uint32_t)planes * (uint32_t)(p.box_rows * PITCH * sizeof(float)));
         for (int q = 0; q < planes; ++q) {
-            int pz = p_first + g * G + q;
+            int pz = first + g * G + q;
             if (p.mode_z != SEPFILT_CONSTANT) pz = remap_index32(p.mode_z, pz, p.nz_in);   // constant: OOB box -> zeros
-            tma_load_plane(raw + ((g & 1) * G + q) * RSLOT, &tmap, x0 - HL, y0 - R, pz, bar);
+            tma_load_plane(raw + ((g & 1) * G + q) * RSLOT, &tmap, cx, cy, pz, bar);
         }
     };
 
@@ -232,7 +235,10 @@ fused3d_kernel(const __grid_constant__ FusedParams p, const __grid_constant__ CU
     // register-bound, and every value kept live across them costs ptxas scheduling freedom (measured:
     // 0.348 -> 0.318 ms on 512^3 in constant mode, which never even runs a patch)
     int* pinfo = reinterpret_cast<int*>(rfull + 4);
-    if (tid == 0) { pinfo[0] = ncell; pinfo[1] = nrow; pinfo[2] = rg0; pinfo[3] = rg1; }
+    if (tid == 0) {
+        pinfo[0] = ncell; pinfo[1] = nrow; pinfo[2] = rg0; pinfo[3] = rg1;
+        pinfo[4] = (ty * (TX / 4) + 31) / 32;               // warps that own output rows
+    }
     if (patching) {
         auto staged_row = [&](int yy) {      // staged row holding the source of row yy; -1 stays zero; -2 not in tile
             const int gy = remap_index32(p.mode_y, y0 - R + yy, p.ny);
@@ -266,8 +272,14 @@ fused3d_kernel(const __grid_constant__ FusedParams p, const __grid_constant__ CU
         const int yy = off / PITCH, c = off - yy * PITCH;
         return fetch_remapped_cell(p, p_first + g * G + q, y0 - R + yy, x0 - HL + c);
     };
-    auto patch = [&](int g) {                              // executed by the NPW patch warps only
+    // patch team: the NPW warps that have no y-pass items plus the warps that own no output row of this
+    // tile (ty < 16): both idle at the start of a phase.  pt = index inside the team, npt = team size.
+    auto patch = [&](int g) {
         const int ncell = pinfo[0], nrow = pinfo[1], rg0 = pinfo[2], rg1 = pinfo[3];
+        const int xw = pinfo[4];                            // warps owning output rows: [0, xw)
+        const int first_free = max(xw, NPW);
+        const int pt = (tid >> 5) < NPW ? tid : tid - (first_free - NPW) * 32;
+        const int npt = (NPW + NW - first_free) * 32;
         int* pcell = meta;
         int* prow = meta + C::MAXCELL;
         // The patch warps share their SM sub-partition with FMA-saturated warps, so every dependent
@@ -275,11 +287,14 @@ fused3d_kernel(const __grid_constant__ FusedParams p, const __grid_constant__ CU
         // stores, and the cold global path is a separate loop.
         const int planes = min(G, n_planes - g * G);
         float* base = raw + (g & 1) * G * RSLOT;
-        for (int ra = tid >> 5; ra < nrow; ra += NPW) {    // rows: float4 copies of the in-range column groups
+        // rows: float4 copies of the in-range column groups; work item = (row, group) in slots of 64 groups
+        for (int i = pt; i < nrow * 64; i += npt) {
+            const int ra = i >> 6, gq = rg0 + (i & 63);
+            if (gq >= rg1) continue;
             const int mr = prow[ra];
             if (mr == NONE) continue;
             const int dst = mr & 0xffff, src = (mr >> 16) & 0xffff;
-            for (int gq = rg0 + (tid & 31); gq < rg1; gq += 32) {
+            {
                 if (src != 0xffff) {
                     float4 v[G];
 #pragma unroll
@@ -298,7 +313,7 @@ fused3d_kernel(const __grid_constant__ FusedParams p, const __grid_constant__ CU
                 }
             }
         }
-        for (int i = tid; i < ncell; i += NPW * 32) {      // column cells
+        for (int i = pt; i < ncell; i += npt) {            // column cells
             const int mc = pcell[i];
             if (mc == NONE) continue;
             const int dst = mc & 0xffff, src = (mc >> 16) & 0xffff;
@@ -363,7 +378,8 @@ fused3d_kernel(const __grid_constant__ FusedParams p, const __grid_constant__ CU
     for (int j = 0; j < (HAS_Z ? 2 * R + 1 : 1); ++j) zacc[j][0] = zacc[j][1] = 0ull;
     const int cg_o = tid % CGW, row_o = tid / CGW;
     const bool owner = row_o < ty && x0 + 4 * cg_o < p.nx;
-    float* out_col = p.out + (size_t)(y0 + row_o) * p.nx + x0 + 4 * cg_o;
+    // the output pointer of the NEXT finished plane, advanced by one plane per step (no 64-bit multiply per plane)
+    float* out_ptr = p.out + (size_t)zb * plane_elems + (size_t)(y0 + row_o) * p.nx + x0 + 4 * cg_o;
     auto xzpass = [&](int g) {
         if (!owner) return;
         const int planes = min(G, n_planes - g * G);
@@ -396,7 +412,8 @@ fused3d_kernel(const __grid_constant__ FusedParams p, const __grid_constant__ CU
                 zacc[2 * R][1] = mul2s(v1, p.wz[0]);
                 const int zo = zb + idx - 2 * R;           // finished output plane
                 if (zo >= zb) {
-                    float4* dst = reinterpret_cast<float4*>(out_col + (size_t)zo * plane_elems);
+                    float4* dst = reinterpret_cast<float4*>(out_ptr);
+                    out_ptr += plane_elems;
                     if (!EPI) {
                         *reinterpret_cast<ulonglong2*>(dst) = make_ulonglong2(zacc[0][0], zacc[0][1]);
                     } else {
@@ -407,7 +424,8 @@ fused3d_kernel(const __grid_constant__ FusedParams p, const __grid_constant__ CU
                     }
                 }
             } else {
-                float4* dst = reinterpret_cast<float4*>(out_col + (size_t)(zb + idx) * plane_elems);
+                float4* dst = reinterpret_cast<float4*>(out_ptr);
+                out_ptr += plane_elems;
                 const float4 v = make_float4(xo[0], xo[1], xo[2], xo[3]);
                 *dst = EPI ? epilogue(p.epilogue, v, dst) : v;
             }
@@ -420,8 +438,9 @@ fused3d_kernel(const __grid_constant__ FusedParams p, const __grid_constant__ CU
     // The TMA of a group is issued two barriers before its first use, the patch runs on the warps that
     // have no y-pass items while the others are busy with the x+z pass, and the y pass comes last in
     // the phase: edge handling and load latency both hide behind arithmetic.
-    auto wait_and_patch = [&](int g) {                      // patch warps, edge tiles only
-        if (!patching || (tid >> 5) >= NPW || g >= n_groups) return;
+    auto wait_and_patch = [&](int g) {                      // patch team, edge tiles only
+        if (!patching || g >= n_groups) return;
+        if ((tid >> 5) >= NPW && (tid >> 5) < pinfo[4]) return;   // a warp with both y items and output rows
 #ifdef SEPFILT_DEBUG_CYCLES
         const long long tw0 = clock64();
 #endif
@@ -436,7 +455,7 @@ fused3d_kernel(const __grid_constant__ FusedParams p, const __grid_constant__ CU
         __syncwarp();
         if ((tid & 31) == 0) mbar_arrive(pdone);
     };
-    if (tid == 0) { mbar_init(&rfull[0], 1); mbar_init(&rfull[1], 1); mbar_init(pdone, NPW); }
+    if (tid == 0) { mbar_init(&rfull[0], 1); mbar_init(&rfull[1], 1); mbar_init(pdone, (uint32_t)(NPW + NW - max((ty * (TX / 4) + 31) / 32, NPW))); }
     __syncthreads();                                       // barriers + patch tables visible
     if (tid == 0) { issue(0); if (n_groups > 1) issue(1); }
     wait_and_patch(0);
