@@ -297,7 +297,8 @@ def run_ours(args):
                        "sharding": "none" if world == 1 else "z-slabs, 8-plane halo exchange over NCCL send/recv",
                        "l2": "input 512 MiB + output 512 MiB per step, both larger than the 126 MB L2; no flush"},
             "roofline": roofline, "e2e": {"value": e2e_value, "unit": UNIT,
-                                           "h2d_bytes_per_step": NZ * NY * NX * 4 * world,
+                                           "h2d_bytes_per_step": (NZ + (2 * 8 * (NZ // 64 - 1) if world == 1 else 0))
+                                                                 * NY * NX * 4 * world,
                                            "d2h_bytes_per_step": NZ * NY * NX * 4 * world,
                                            "steps": e2e_steps,
                                            "api": "cupyimg_b200.host.gaussian_filter_host (pinned host in / out, "
