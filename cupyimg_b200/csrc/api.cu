@@ -5,6 +5,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 
@@ -199,6 +200,12 @@ int sepfilt_correlate1d(const sepfilt_tensor* in, const sepfilt_tensor* out,
         g.n_in = in->shape[axis];
         g.n_out = out->shape[axis];
         g.shift = in_offset - pass->origin;
+        static const bool no_stream = getenv("SEPFILT_NO_STREAM") != nullptr;   // test / tuning aid
+        if (!no_stream && exact_stream_supported(g, pass->ntaps, sym)) {
+            cudaError_t e = launch_exact_stream(g, pass->taps, pass->ntaps, sym, pass->mode, cval, s);
+            if (e != cudaSuccess) return fail_cuda(e, "exact_stream launch");
+            return SEPFILT_OK;
+        }
         if (exact_tiled_supported(g, pass->ntaps, sym)) {
             cudaError_t e = launch_exact_tiled(g, pass->taps, pass->ntaps, sym, pass->mode, cval, s);
             if (e != cudaSuccess) return fail_cuda(e, "exact_tiled launch");

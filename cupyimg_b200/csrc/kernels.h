@@ -41,6 +41,12 @@ bool        exact_tiled_supported(const ExactTiledGeom& g, int K, int symmetric)
 cudaError_t launch_exact_tiled(const ExactTiledGeom& g, const double* taps, int K, int symmetric, int mode,
                                double cval, cudaStream_t s);
 
+// ---- exact path, register streaming (exact_stream.cu): dtype-preserving u8 / i16 / u16 / f32 / f64,
+//      radius <= 8, vector-aligned geometry; same bits as the two kernels above ----
+bool        exact_stream_supported(const ExactTiledGeom& g, int K, int symmetric);
+cudaError_t launch_exact_stream(const ExactTiledGeom& g, const double* taps, int K, int symmetric, int mode,
+                                double cval, cudaStream_t s);
+
 // ---- f32 tiled 1-D passes (f32_1d.cu): C-contiguous (outer, n, inner) view ----
 struct F32Taps {
     int32_t radius;                       // R: taps cover offsets -R..R (zero padded)
