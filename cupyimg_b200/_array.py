@@ -114,6 +114,14 @@ class DevArray:
         t.device = self.device
         return t
 
+    def component(self, which):
+        """Real (0) / imaginary (1) part of a complex array as a strided real view (no copy)."""
+        if self.dtype.kind != "c":
+            raise TypeError("component() needs a complex array")
+        part = np.dtype("float32") if self.dtype.itemsize == 8 else np.dtype("float64")
+        return DevArray(self.ptr + which * part.itemsize, self.shape, self.strides, part, self.device,
+                        self.obj, self.foreign)
+
     def view_axis_window(self, axis, start, length):
         """Sub-view [start, start+length) along ``axis`` (no copy)."""
         shape = list(self.shape)

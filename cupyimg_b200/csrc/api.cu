@@ -360,7 +360,7 @@ int sepfilt_separable_f32(const sepfilt_tensor* in, const sepfilt_tensor* out,
 
 int sepfilt_gradmag_step(void* acc, const void* a, int64_t n, int dtype, int op, void* stream)
 {
-    if (n < 0 || op < 0 || op > 3 || dtype < SEPFILT_I8 || dtype > SEPFILT_F64)
+    if (n < 0 || op < 0 || op > 4 || dtype < SEPFILT_I8 || dtype > SEPFILT_F64)
         return fail(SEPFILT_ERR_INVALID, "bad gradmag_step arguments");
     if (n == 0) return SEPFILT_OK;
     if (!acc || !a) return fail(SEPFILT_ERR_INVALID, "NULL data pointer");

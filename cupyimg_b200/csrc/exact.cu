@@ -102,11 +102,13 @@ gradmag_step_kernel(T* __restrict__ acc, const T* __restrict__ a, int64_t n, int
             if (op == 0) acc[i] = __fmul_rn(a[i], a[i]);
             else if (op == 1) acc[i] = __fadd_rn(acc[i], __fmul_rn(a[i], a[i]));
             else if (op == 2) acc[i] = __fsqrt_rn(acc[i]);
+            else if (op == 4) acc[i] = __fsub_rn(acc[i], a[i]);
             else acc[i] = __fadd_rn(acc[i], a[i]);
         } else if constexpr (std::is_same<T, double>::value) {
             if (op == 0) acc[i] = __dmul_rn(a[i], a[i]);
             else if (op == 1) acc[i] = __dadd_rn(acc[i], __dmul_rn(a[i], a[i]));
             else if (op == 2) acc[i] = __dsqrt_rn(acc[i]);
+            else if (op == 4) acc[i] = __dsub_rn(acc[i], a[i]);
             else acc[i] = __dadd_rn(acc[i], a[i]);
         } else {                                                        // integers wrap
             const uint64_t x = (uint64_t)(int64_t)a[i];
@@ -114,6 +116,7 @@ gradmag_step_kernel(T* __restrict__ acc, const T* __restrict__ a, int64_t n, int
             if (op == 0) acc[i] = (T)xx;
             else if (op == 1) acc[i] = (T)((uint64_t)(int64_t)acc[i] + xx);
             else if (op == 2) store_cast(reinterpret_cast<char*>(acc + i), dtype, __dsqrt_rn((double)acc[i]));
+            else if (op == 4) acc[i] = (T)((uint64_t)(int64_t)acc[i] - x);
             else acc[i] = (T)((uint64_t)(int64_t)acc[i] + x);
         }
     }

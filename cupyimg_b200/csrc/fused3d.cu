@@ -136,11 +136,10 @@ __device__ __forceinline__ void tma_load_plane(void* dst, const CUtensorMap* map
 // generic_gradient_magnitude staging in the output dtype (filters.py:1187-1201), fused into the store:
 // 1: out = v*v   2: out += v*v   3: out = sqrt(out + v*v); explicit _rn ops, no FMA contraction, so
 // the float32 roundings are the ones of the reference's separate multiply / add / sqrt kernels.
-__device__ __forceinline__ float4 epilogue(int mode, float4 v, const float4* dst)
+__device__ __forceinline__ float4 epilogue(int mode, float4 v, const float4 old)
 {
     float4 sq = make_float4(__fmul_rn(v.x, v.x), __fmul_rn(v.y, v.y), __fmul_rn(v.z, v.z), __fmul_rn(v.w, v.w));
     if (mode == 1) return sq;
-    const float4 old = *dst;
     sq = make_float4(__fadd_rn(old.x, sq.x), __fadd_rn(old.y, sq.y), __fadd_rn(old.z, sq.z), __fadd_rn(old.w, sq.w));
     if (mode == 2) return sq;
     return make_float4(__fsqrt_rn(sq.x), __fsqrt_rn(sq.y), __fsqrt_rn(sq.z), __fsqrt_rn(sq.w));
@@ -387,6 +386,10 @@ fused3d_kernel(const __grid_constant__ FusedParams p, const __grid_constant__ CU
         for (int q = 0; q < G; ++q) {
             if (q >= planes) break;
             const float* src = ybuf + ((g & 1) * G + q) * YSLOT + row_o * PITCH + 4 * cg_o;
+            // gradient-magnitude accumulation: the running sum of squares of the voxel this step finishes
+            // is requested before the arithmetic of the plane, not at the store
+            float4 old = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (EPI && p.epilogue >= 2 && (!HAS_Z || g * G + q >= 2 * R)) old = *reinterpret_cast<const float4*>(out_ptr);
             float win[4 * NV];
 #pragma unroll
             for (int i = 0; i < NV; ++i) {
@@ -420,14 +423,14 @@ fused3d_kernel(const __grid_constant__ FusedParams p, const __grid_constant__ CU
                         float4 v;
                         asm("mov.b64 {%0, %1}, %2;" : "=f"(v.x), "=f"(v.y) : "l"(zacc[0][0]));
                         asm("mov.b64 {%0, %1}, %2;" : "=f"(v.z), "=f"(v.w) : "l"(zacc[0][1]));
-                        *dst = epilogue(p.epilogue, v, dst);
+                        *dst = epilogue(p.epilogue, v, old);
                     }
                 }
             } else {
                 float4* dst = reinterpret_cast<float4*>(out_ptr);
                 out_ptr += plane_elems;
                 const float4 v = make_float4(xo[0], xo[1], xo[2], xo[3]);
-                *dst = EPI ? epilogue(p.epilogue, v, dst) : v;
+                *dst = EPI ? epilogue(p.epilogue, v, old) : v;
             }
         }
     };
@@ -479,7 +482,7 @@ int radius_bucket(int r)
     // radius 16 (33 taps) is NOT fused: 33 z accumulators x 4 columns force 256-thread CTAs on 64-wide
     // tiles (1.5x y-pass halo work, 2 warps per sub-partition) and measured 1.25 ms on 512^3 against
     // 1.02 ms for three tiled passes
-    static const int buckets[] = {1, 2, 4, 8};
+    static const int buckets[] = {1, 2, 3, 4, 6, 8};
     for (int b : buckets) if (r <= b) return b;
     return -1;
 }
@@ -658,8 +661,12 @@ static cudaError_t launch_one(const FusedVolume& v, const F32Taps taps[3], int e
     case 1 * 2 + 1: return launch_r<1, true>(v, p, s);
     case 2 * 2 + 0: return launch_r<2, false>(v, p, s);
     case 2 * 2 + 1: return launch_r<2, true>(v, p, s);
+    case 3 * 2 + 0: return launch_r<3, false>(v, p, s);
+    case 3 * 2 + 1: return launch_r<3, true>(v, p, s);
     case 4 * 2 + 0: return launch_r<4, false>(v, p, s);
     case 4 * 2 + 1: return launch_r<4, true>(v, p, s);
+    case 6 * 2 + 0: return launch_r<6, false>(v, p, s);
+    case 6 * 2 + 1: return launch_r<6, true>(v, p, s);
     case 8 * 2 + 0: return launch_r<8, false>(v, p, s);
     case 8 * 2 + 1: return launch_r<8, true>(v, p, s);
     default: return cudaErrorInvalidValue;

@@ -90,40 +90,61 @@ def _check_dtype_mode(dtype_mode):
     return dtype_mode
 
 
-def _get_output(output, inp, shape=None):
-    """_util._get_output (_util.py:43-81) without the memset: returns (DevArray, user_owned)."""
+_COMPLEX = (np.dtype("complex64"), np.dtype("complex128"))
+
+
+def _get_output(output, inp, shape=None, complex_output=None):
+    """_util._get_output (_util.py:43-81) without the memset: returns (DevArray, user_owned).
+    A complex input or complex weights need a complex output (_util.py:52-58, :69-75); with
+    ``output=None`` it is promote_types(input, complex64) (_util.py:66-67)."""
     shape = inp.shape if shape is None else tuple(shape)
+    if complex_output is None:
+        complex_output = inp.dtype.kind == "c"
+
+    def check(dt):
+        if complex_output:
+            if dt.kind != "c":
+                raise RuntimeError("output must have complex dtype if either the input or "
+                                   "weights are complex-valued.")
+            if dt not in _COMPLEX:
+                raise RuntimeError("array type {} not supported".format(dt))
+        elif dt not in _ffi.DTYPE_CODES or dt == np.dtype("bool"):
+            raise RuntimeError("array type {} not supported".format(dt))
+
     if output is None:
-        return _array.empty(shape, inp.dtype, inp.device), False
+        dt = np.promote_types(inp.dtype, np.complex64) if complex_output else inp.dtype
+        return _array.empty(shape, dt, inp.device), False
     if _array.is_device_array(output):
         out = _array.ingest(output, "output")
         if out.shape != shape:
             raise _array.OutputShapeError("output shape not correct")
         if out.device != inp.device:
             raise RuntimeError("output must live on the same device as the input")
-        if out.dtype not in _ffi.DTYPE_CODES or out.dtype == np.dtype("bool"):
-            raise RuntimeError("array type {} not supported".format(out.dtype))
+        check(out.dtype)
         return out, True
     dt = _array.to_numpy_dtype(output)
-    if dt not in _ffi.DTYPE_CODES or dt == np.dtype("bool"):
-        raise RuntimeError("array type {} not supported".format(dt))
+    check(dt)
     return _array.empty(shape, dt, inp.device), False
 
 
 def _ingest_input(input):
     inp = _array.ingest(input, "input")
-    if inp.dtype.kind == "c":
-        raise NotImplementedError("complex-valued arrays are not supported yet")
-    if inp.dtype not in _ffi.DTYPE_CODES:
+    if inp.dtype not in _ffi.DTYPE_CODES and inp.dtype not in _COMPLEX:
         raise RuntimeError("array type {} not supported".format(inp.dtype))
     return inp
 
 
 def _host_taps(weights):
-    w = _array.host_weights(weights)
-    if w.dtype.kind == "c":
-        raise NotImplementedError("complex-valued weights are not supported yet")
-    return w
+    return _array.host_weights(weights)
+
+
+def _split_cval(cval, complex_input):
+    """Complex arrays are filtered by real and imaginary component, each with its part of cval."""
+    if isinstance(cval, complex) or np.iscomplexobj(cval):
+        if not complex_input:
+            raise ValueError("Cannot provide a complex-valued cval when the input is real.")
+        return float(np.real(cval)), float(np.imag(cval))
+    return float(cval), 0.0
 
 
 # ----------------------------------------------------------------------------
@@ -228,6 +249,18 @@ def _run_passes(inp, out, specs, cval, dtype_mode):
     temp + copy-back per in-place pass (_filters_core.py:148-155)."""
     if out.size == 0:
         return out
+    if inp.dtype.kind == "c" or out.dtype.kind == "c":
+        # real taps act on the real and the imaginary component independently (the reference's kernel
+        # does the complex multiply-add with a real weight, _filters_core.py:239-312): two real runs
+        # over strided component views, every pass rounded to the component dtype like the complex store
+        if inp.dtype.kind != "c" or out.dtype.kind != "c":
+            raise RuntimeError("output must have complex dtype if either the input or "
+                               "weights are complex-valued.")
+        cre, cim = _split_cval(cval, True)
+        _run_passes(inp.component(0), out.component(0), specs, cre, dtype_mode)
+        _run_passes(inp.component(1), out.component(1), specs, cim, dtype_mode)
+        return out
+    cval, _ = _split_cval(cval, False)
     exact = dtype_mode == "ndimage"
     if not specs:
         if inp.may_overlap(out):
@@ -297,6 +330,34 @@ def _run_passes_window(inp, out, specs, cval, dtype_mode, in_offset0):
     return out
 
 
+def _gradient_magnitude_window(inp, out, smooth, deriv, cval, dtype_mode, in_offset0):
+    """sqrt(sum_a (D_a prod_{b != a} S_b inp)^2) for an output that windows the input along axis 0
+    (the z-slab call of the sharded path).  ``smooth`` / ``deriv`` hold one pass per axis in
+    increasing axis order.  One fused launch per axis for float32 volumes; otherwise the
+    reference's staging (filters.py:1187-1201): one windowed separable filter per axis into a
+    temporary, squares / sum / sqrt in the output dtype."""
+    if out.size == 0:
+        return out
+    exact = dtype_mode == "ndimage"
+    if _fused_candidate(inp, out, smooth, exact, gradmag=True) and len(smooth) == inp.ndim \
+            and _try_fused(inp, out, smooth, cval, dspecs=deriv, in_offset0=in_offset0):
+        return out
+    acc = out if out.c_contiguous() else _array.empty(out.shape, out.dtype, out.device)
+    for i, d in enumerate(deriv):
+        specs = [d if s.axis == d.axis else s for s in smooth]
+        if i == 0:
+            _run_passes_window(inp, acc, specs, cval, dtype_mode, in_offset0)
+            _accumulate(acc, acc, 0)
+        else:
+            tmp = _array.empty(out.shape, out.dtype, out.device)
+            _run_passes_window(inp, tmp, specs, cval, dtype_mode, in_offset0)
+            _accumulate(acc, tmp, 1)
+    _accumulate(acc, acc, 2)
+    if acc is not out:
+        _copy_cast(acc, out)
+    return out
+
+
 # ----------------------------------------------------------------------------
 # public API
 # ----------------------------------------------------------------------------
@@ -313,8 +374,45 @@ def correlate1d(input, weights, axis=-1, output=None, mode="reflect", cval=0.0, 
     axis = _normalize_axis_index(axis, inp.ndim)
     origin = _check_origin(origin, w.size)
     mode_code = _check_mode(mode)
+    if w.dtype.kind == "c":
+        return _correlate1d_complex_taps(inp, w.conj(), axis, output, mode_code, cval, origin, dtype_mode)
     out, _ = _get_output(output, inp)
     _run_passes(inp, out, [_PassSpec(axis, w, origin, mode_code)], cval, dtype_mode)
+    return _array.export(out, inp)
+
+
+def _correlate1d_complex_taps(inp, w, axis, output, mode_code, cval, origin, dtype_mode):
+    """Complex weights (already conjugated: correlation conjugates the weights, not the input —
+    filters.py:467-469): a linear combination of real passes, the way scipy evaluates it
+    (scipy/ndimage/_filters.py ``_complex_via_real_components``)."""
+    out, _ = _get_output(output, inp, complex_output=True)
+    if out.size == 0:
+        return _array.export(out, inp)
+    w_re = _PassSpec(axis, np.ascontiguousarray(w.real), origin, mode_code)
+    w_im = _PassSpec(axis, np.ascontiguousarray(w.imag), origin, mode_code)
+    o_re, o_im = out.component(0), out.component(1)
+    if inp.dtype.kind != "c":
+        cval, _ = _split_cval(cval, False)
+        if inp.may_overlap(out):
+            raise RuntimeError("in-place filtering of a real array with complex weights is not possible")
+        _run_passes(inp, o_re, [w_re], cval, dtype_mode)
+        _run_passes(inp, o_im, [w_im], cval, dtype_mode)
+        return _array.export(out, inp)
+    cre, cim = _split_cval(cval, True)
+    i_re, i_im = inp.component(0), inp.component(1)
+    part = o_re.dtype
+
+    def one(src, spec, c):
+        tmp = _array.empty(out.shape, part, out.device)
+        _run_passes(src, tmp, [spec], c, dtype_mode)
+        return tmp
+
+    re = one(i_re, w_re, cre)
+    _accumulate(re, one(i_im, w_im, cim), 4)          # real part: re*re - im*im
+    im = one(i_re, w_im, cre)
+    _accumulate(im, one(i_im, w_re, cim), 3)          # imaginary part: re*im + im*re
+    _copy_cast(re, o_re)
+    _copy_cast(im, o_im)
     return _array.export(out, inp)
 
 
@@ -336,6 +434,8 @@ def convolve1d(input, weights, axis=-1, output=None, mode="reflect", cval=0.0, o
     origin = -origin
     if not w.size & 1:
         origin -= 1
+    if w.dtype.kind == "c":
+        w = w.conj()                  # convolution does not conjugate: undo correlate1d's conjugation
     return correlate1d(input, w, axis, output, mode, cval, origin, dtype_mode=dtype_mode)
 
 
@@ -520,6 +620,15 @@ def _generic_axis_reduce(input, derivative, output, mode, cval, extra_arguments,
         extra_keywords = {}
     inp = _ingest_input(input)
     out, _ = _get_output(output, inp)
+    if inp.dtype.kind == "c":
+        if magnitude:
+            raise NotImplementedError("gradient magnitude of a complex array is not supported")
+        # a sum of per-axis real-tap filters is linear: filter the components
+        cre, cim = _split_cval(cval, True)
+        for k, c in ((0, cre), (1, cim)):
+            _generic_axis_reduce(inp.component(k), derivative, out.component(k), mode, c,
+                                 extra_arguments, extra_keywords, magnitude)
+        return _array.export(out, inp)
     ndim = inp.ndim
     if ndim == 0 or out.size == 0:
         if out.size:

@@ -147,6 +147,42 @@ class ZSlabFilter:
             compute = _cuda_compute(specs, self.cval, dtype_mode)
         return self.run(x, output, compute)
 
+    def separable(self, x, specs, output=None, dtype_mode=None, compute=None):
+        """Sharded run of any list of 1-D passes (``filters._PassSpec``, increasing axis order)."""
+        if output is None:
+            output = torch.empty_like(x)
+        if compute is None:
+            self._check_radius(specs)
+            compute = _cuda_compute(list(specs), self.cval, dtype_mode)
+        return self.run(x, output, compute)
+
+    def sobel(self, x, axis=-1, output=None, dtype_mode=None, compute=None, smooth=(1.0, 2.0, 1.0)):
+        """Sharded ``sobel`` (``smooth=(1, 1, 1)``: ``prewitt``), reference filters.py:828-941."""
+        axis = axis % 3
+        modes = [_filters._check_mode(m) for m in _filters._normalize_sequence(self.mode, 3)]
+        specs = [_filters._PassSpec(a, np.array([-1.0, 0.0, 1.0]) if a == axis else np.asarray(smooth, np.float64),
+                                    0, modes[a]) for a in range(3)]
+        return self.separable(x, specs, output, dtype_mode, compute)
+
+    def gaussian_gradient_magnitude(self, x, sigma, output=None, truncate=4.0, dtype_mode=None, compute=None):
+        """Sharded ``gaussian_gradient_magnitude`` (reference filters.py:1207-1252): the three
+        derivative filters share ONE halo exchange of raw planes; square / sum / sqrt stay local."""
+        if output is None:
+            output = torch.empty_like(x)
+        if compute is None:
+            inp = _array.ingest(x)
+            smooth = _filters._gaussian_specs(inp, sigma, 0, self.mode, truncate)
+            deriv = _filters._gaussian_specs(inp, sigma, 1, self.mode, truncate)
+            if len(smooth) != 3 or len(deriv) != 3:
+                raise ValueError("sharded gradient magnitude needs sigma > 0 on every axis")
+            self._check_radius(deriv)
+            cval = self.cval
+
+            def compute(src, dst, in_offset0):
+                _filters._gradient_magnitude_window(_array.ingest(src), _array.ingest(dst), smooth, deriv,
+                                                    cval, dtype_mode, in_offset0)
+        return self.run(x, output, compute)
+
     def uniform_filter(self, x, size=3, origin=0, output=None, dtype_mode=None, compute=None):
         """Sharded ``uniform_filter``."""
         if output is None:

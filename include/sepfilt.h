@@ -158,6 +158,8 @@ SEPFILT_API int sepfilt_separable_f32_supported(const sepfilt_tensor* in, const 
  *   op 1: acc += a*a          (further axes)
  *   op 2: acc  = sqrt(acc)    (final, "unsafe" cast back to the dtype)
  *   op 3: acc += a            (generic_laplace accumulation, filters.py:1024-1035)
+ *   op 4: acc -= a            (real part of a complex x complex correlation: re*re - im*im; the
+ *                              reference does the complex multiply-add in the kernel, filters.py:467-469)
  * a and acc are C-contiguous arrays of `dtype` with n elements. */
 SEPFILT_API int sepfilt_gradmag_step(void* acc, const void* a, int64_t n, int dtype, int op, void* stream);
 

@@ -152,8 +152,50 @@ def _line_pass(input, output, axis, w, K, origin, mode, cval, uniform=0, in_offs
     return output
 
 
+def _complex_output(output, input):
+    """_util._get_output's complex rule (_util.py:52-58, :66-75)."""
+    if output is None:
+        return np.zeros(input.shape, np.promote_types(input.dtype, np.complex64))
+    if isinstance(output, np.ndarray):
+        if output.shape != input.shape:
+            raise RuntimeError("output shape not correct")
+        if output.dtype.kind != "c":
+            raise RuntimeError("output must have complex dtype")
+        return output
+    if np.dtype(output).kind != "c":
+        raise RuntimeError("output must have complex dtype")
+    return np.zeros(input.shape, np.dtype(output))
+
+
+def _correlate1d_complex(input, weights, axis, output, mode, cval, origin):
+    """Complex input and / or weights.  The reference conjugates the weights (filters.py:467-469) and
+    lets its kernel do the complex multiply-add; restated here the way scipy evaluates the same sum,
+    as a linear combination of real passes (scipy/ndimage/_filters.py, _complex_via_real_components)."""
+    if weights.dtype.kind == "c":
+        weights = weights.conj().astype(np.complex128)
+    out = _complex_output(output, input)
+    kw = dict(axis=axis, mode=mode, origin=origin)
+    if input.dtype.kind == "c" and weights.dtype.kind == "c":
+        correlate1d(input.real, weights.real, output=out.real, cval=np.real(cval), **kw)
+        out.real -= correlate1d(input.imag, weights.imag, cval=np.imag(cval), **kw)
+        correlate1d(input.real, weights.imag, output=out.imag, cval=np.real(cval), **kw)
+        out.imag += correlate1d(input.imag, weights.real, cval=np.imag(cval), **kw)
+    elif input.dtype.kind == "c":
+        correlate1d(input.real, weights, output=out.real, cval=np.real(cval), **kw)
+        correlate1d(input.imag, weights, output=out.imag, cval=np.imag(cval), **kw)
+    else:
+        if np.iscomplexobj(cval):
+            raise ValueError("Cannot provide a complex-valued cval when the input is real.")
+        correlate1d(input, weights.real, output=out.real, cval=cval, **kw)
+        correlate1d(input, weights.imag, output=out.imag, cval=cval, **kw)
+    return out
+
+
 def correlate1d(input, weights, axis=-1, output=None, mode="reflect", cval=0.0, origin=0):
     input = np.asarray(input)
+    weights = np.asarray(weights)
+    if input.dtype.kind == "c" or weights.dtype.kind == "c":
+        return _correlate1d_complex(input, weights, axis, output, mode, cval, origin)
     weights = np.asarray(weights, np.float64)
     if weights.ndim != 1 or weights.size < 1:
         raise RuntimeError("no filter weights given")
@@ -165,7 +207,8 @@ def correlate1d(input, weights, axis=-1, output=None, mode="reflect", cval=0.0, 
 
 
 def convolve1d(input, weights, axis=-1, output=None, mode="reflect", cval=0.0, origin=0):
-    weights = np.asarray(weights, np.float64)[::-1]
+    weights = np.asarray(weights)
+    weights = (weights.conj() if weights.dtype.kind == "c" else weights.astype(np.float64))[::-1]
     origin = -origin
     if weights.size and not weights.size & 1:
         origin -= 1

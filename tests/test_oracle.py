@@ -127,3 +127,30 @@ def test_reference_executed_vectors():
         got = call_filter(oracle, func, x, kwargs)
         n[check_against_reference(func, x, got, ref)] += 1
     assert n["checked"] > 1000 and n["skipped"] < 0.02 * n["checked"]
+
+
+def test_complex_oracle_matches_scipy():
+    """Complex input and / or weights (the reference's test_correlate1d_complex,
+    tests/test_ndimage_vs_scipy.py:114-126, sweeps exactly this dtype matrix): the oracle's
+    restatement by real components against scipy, bit for bit, with non-trivial imaginary parts."""
+    import scipy.ndimage as sn
+    rng = np.random.default_rng(0)
+    types = [np.float32, np.float64, np.complex64, np.complex128]
+    for dx, dh in itertools.product(types, types):
+        cx, ch = np.dtype(dx).kind == "c", np.dtype(dh).kind == "c"
+        if not (cx or ch):
+            continue
+        x = (rng.standard_normal((5, 9)) + (1j * rng.standard_normal((5, 9)) if cx else 0)).astype(dx)
+        for len_h in (1, 2, 5, 12):
+            h = (rng.standard_normal(len_h) + (1j * rng.standard_normal(len_h) if ch else 0)).astype(dh)
+            for mode in ("reflect", "constant", "nearest", "mirror", "wrap"):
+                cval = (0.5 - 2j) if cx else 0.5
+                for fn in ("correlate1d", "convolve1d"):
+                    got = getattr(oracle, fn)(x, h, axis=1, mode=mode, cval=cval)
+                    want = getattr(sn, fn)(x, h, axis=1, mode=mode, cval=cval)
+                    assert got.dtype == want.dtype
+                    np.testing.assert_array_equal(got, want)
+    with pytest.raises(RuntimeError):
+        oracle.correlate1d(np.ones(4, np.complex64), [1.0, 2.0], output=np.float64)
+    with pytest.raises(ValueError):
+        oracle.correlate1d(np.ones(4), np.array([1.0, 2.0j]), cval=1j, mode="constant")

@@ -37,6 +37,26 @@ def _oracle_window_compute(mode):
     return compute
 
 
+def _oracle_gradmag_window_compute(mode, sigma):
+    """Per-slab gradient magnitude by the oracle: the three derivative filters on the windowed slab."""
+    lw = int(4 * sigma + 0.5)
+    g = oracle.gaussian_kernel1d(sigma, 0, lw)[::-1]
+    d = oracle.gaussian_kernel1d(sigma, 1, lw)[::-1]
+
+    def compute(src, dst, in_offset0):
+        s = src.numpy()
+        acc = np.zeros(tuple(dst.shape), np.float32)
+        for a in range(3):
+            w = [d if b == a else g for b in range(3)]
+            out = np.empty(tuple(dst.shape), np.float32)
+            oracle._line_pass(s, out, 0, w[0], w[0].size, 0, mode, 0.0, in_offset=in_offset0)
+            for axis in (1, 2):
+                out = oracle.correlate1d(out, w[axis], axis=axis, mode=mode)
+            acc = acc + out * out
+        dst.copy_(torch.from_numpy(np.sqrt(acc)))
+    return compute
+
+
 def _worker(rank, world, port, mode, result_dir):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -53,6 +73,10 @@ def _worker(rank, world, port, mode, result_dir):
         # a second call reuses the plan's halo buffers
         out2 = plan.gaussian_filter(x, SIGMA, compute=_oracle_window_compute(mode))
         ok = ok and np.array_equal(out2.numpy(), out.numpy())
+        # gradient magnitude (C4's filter): one halo exchange serves the three derivative filters
+        want3 = oracle.gaussian_gradient_magnitude(vol, SIGMA, mode=mode)
+        out3 = plan.gaussian_gradient_magnitude(x, SIGMA, compute=_oracle_gradmag_window_compute(mode, SIGMA))
+        ok = ok and np.array_equal(out3.numpy(), want3[rank * NZ:(rank + 1) * NZ])
         with open(os.path.join(result_dir, "rank%d" % rank), "w") as f:
             f.write("ok" if ok else "mismatch")
     finally:

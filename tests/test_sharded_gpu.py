@@ -44,6 +44,20 @@ def _worker(rank, world, port, result_dir):
                 got2 = plan.uniform_filter(x, 5)
                 want2 = ndi.uniform_filter(vol.to(dev), 5, mode=mode)
                 ok = ok and torch.equal(got2, want2[rank * nz:(rank + 1) * nz])
+            # C4's filter: three derivative filters behind one halo exchange
+            plan = sharded.ZSlabFilter(x.shape, radius=6, mode=mode, device=dev)
+            got3 = plan.gaussian_gradient_magnitude(x, 1.5)
+            want3 = ndi.gaussian_gradient_magnitude(vol.to(dev), 1.5, mode=mode)
+            ok = ok and torch.equal(got3, want3[rank * nz:(rank + 1) * nz])
+            got4 = plan.sobel(x, 0)
+            want4 = ndi.sobel(vol.to(dev), 0, mode=mode)
+            ok = ok and torch.equal(got4, want4[rank * nz:(rank + 1) * nz])
+            # exact (float64-accumulate) staging of the same filter on an integer volume
+            vi = (vol * 1000).to(torch.int32)
+            plan_i = sharded.ZSlabFilter(x.shape, radius=6, mode=mode, device=dev, dtype=torch.int32)
+            got5 = plan_i.gaussian_gradient_magnitude(vi[rank * nz:(rank + 1) * nz].to(dev), 1.5)
+            want5 = ndi.gaussian_gradient_magnitude(vi.to(dev), 1.5, mode=mode)
+            ok = ok and torch.equal(got5, want5[rank * nz:(rank + 1) * nz])
         with open(os.path.join(result_dir, "rank%d" % rank), "w") as f:
             f.write("ok" if ok else "mismatch")
     finally:
@@ -69,3 +83,5 @@ def test_world_size_one_plan():
     x = torch.rand((24, 32, 64), device="cuda")
     plan = sharded.ZSlabFilter(x.shape, radius=8, device="cuda")
     assert torch.equal(plan.gaussian_filter(x, 2.0), ndi.gaussian_filter(x, 2.0))
+    assert torch.equal(plan.gaussian_gradient_magnitude(x, 1.5), ndi.gaussian_gradient_magnitude(x, 1.5))
+    assert torch.equal(plan.sobel(x, 1), ndi.sobel(x, 1))
