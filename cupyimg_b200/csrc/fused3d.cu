@@ -350,8 +350,6 @@ fused3d_kernel(const __grid_constant__ FusedParams p, const __grid_constant__ CU
 #endif
         if (!y_item || g * G + yq >= n_planes) return;
         u64 acc[RY][2];
-#pragma unroll
-        for (int o = 0; o < RY; ++o) acc[o][0] = acc[o][1] = 0ull;
         const float* src = raw + ((g & 1) * G + yq) * RSLOT + (yhalf * RY) * PITCH + 4 * ycg;
 #pragma unroll
         for (int j = 0; j < RY + 2 * R; ++j) {
@@ -359,7 +357,10 @@ fused3d_kernel(const __grid_constant__ FusedParams p, const __grid_constant__ CU
 #pragma unroll
             for (int o = 0; o < RY; ++o) {
                 const int k = j - o;
-                if (k >= 0 && k <= 2 * R) {
+                if (k == 0) {                               // first tap initialises: no zeroing of 2 RY register pairs
+                    acc[o][0] = mul2s(v.x, p.wy[0]);
+                    acc[o][1] = mul2s(v.y, p.wy[0]);
+                } else if (k > 0 && k <= 2 * R) {
                     acc[o][0] = fma2s(v.x, p.wy[k], acc[o][0]);
                     acc[o][1] = fma2s(v.y, p.wy[k], acc[o][1]);
                 }
@@ -372,9 +373,18 @@ fused3d_kernel(const __grid_constant__ FusedParams p, const __grid_constant__ CU
     };
 
     // ---- x pass + z scatter of one group, plane by plane; 2R+1 shifting z accumulators per column
-    u64 zacc[HAS_Z ? 2 * R + 1 : 1][2];
+    // Z accumulators: 2R+1 logical accumulators in 2R+1 + (G-1) physical slots.  Within a G-plane group
+    // every plane updates in place (logical j of plane q lives in slot j + q: the shift costs nothing);
+    // the LAST plane of the group writes logical j back to slot j, in ascending j so that no live value
+    // is overwritten.  The loop-carried naming is therefore the same at the top of every group.  (With
+    // 2R+1 slots the compiler had to rotate all of them back at the end of each group: ~17 MOV /
+    // IMAD.MOV per thread and plane at R = 8, 13 % of the executed instructions, IMAD.MOV on the FMA
+    // pipe.  17 phase-specialised loop bodies with zero moves were measured too: 207 KB of code thrash
+    // the 32 KB instruction cache, 0.346 -> 0.568 ms.)
+    constexpr int ZW = HAS_Z ? 2 * R + 1 : 1, ZS = HAS_Z ? ZW + G - 1 : 1;
+    u64 zacc[ZS][2];
 #pragma unroll
-    for (int j = 0; j < (HAS_Z ? 2 * R + 1 : 1); ++j) zacc[j][0] = zacc[j][1] = 0ull;
+    for (int j = 0; j < ZS; ++j) zacc[j][0] = zacc[j][1] = 0ull;
     const int cg_o = tid % CGW, row_o = tid / CGW;
     const bool owner = row_o < ty && x0 + 4 * cg_o < p.nx;
     // the output pointer of the NEXT finished plane, advanced by one plane per step (no 64-bit multiply per plane)
@@ -418,23 +428,26 @@ fused3d_kernel(const __grid_constant__ FusedParams p, const __grid_constant__ CU
             const int idx = g * G + q;                     // plane index within this CTA's march
             if (HAS_Z) {
                 const u64 v0 = pack2(xo[0], xo[1]), v1 = pack2(xo[2], xo[3]);
+                constexpr int LASTQ = G - 1;
+                const int fs = q == LASTQ ? 0 : q + 1;        // slot of the voxel this plane finishes
 #pragma unroll
                 for (int j = 0; j < 2 * R; ++j) {
-                    zacc[j][0] = fma2s(v0, p.wz[2 * R - j], zacc[j + 1][0]);
-                    zacc[j][1] = fma2s(v1, p.wz[2 * R - j], zacc[j + 1][1]);
+                    const int src_slot = j + 1 + q, dst_slot = q == LASTQ ? j : j + 1 + q;
+                    zacc[dst_slot][0] = fma2s(v0, p.wz[2 * R - j], zacc[src_slot][0]);
+                    zacc[dst_slot][1] = fma2s(v1, p.wz[2 * R - j], zacc[src_slot][1]);
                 }
-                zacc[2 * R][0] = mul2s(v0, p.wz[0]);
-                zacc[2 * R][1] = mul2s(v1, p.wz[0]);
+                zacc[q == LASTQ ? 2 * R : 2 * R + 1 + q][0] = mul2s(v0, p.wz[0]);
+                zacc[q == LASTQ ? 2 * R : 2 * R + 1 + q][1] = mul2s(v1, p.wz[0]);
                 const int zo = zb + idx - 2 * R;           // finished output plane
                 if (zo >= zb) {
                     float4* dst = reinterpret_cast<float4*>(out_ptr);
                     out_ptr += plane_elems;
                     if (!EPI) {
-                        *reinterpret_cast<ulonglong2*>(dst) = make_ulonglong2(zacc[0][0], zacc[0][1]);
+                        *reinterpret_cast<ulonglong2*>(dst) = make_ulonglong2(zacc[fs][0], zacc[fs][1]);
                     } else {
                         float4 v;
-                        asm("mov.b64 {%0, %1}, %2;" : "=f"(v.x), "=f"(v.y) : "l"(zacc[0][0]));
-                        asm("mov.b64 {%0, %1}, %2;" : "=f"(v.z), "=f"(v.w) : "l"(zacc[0][1]));
+                        asm("mov.b64 {%0, %1}, %2;" : "=f"(v.x), "=f"(v.y) : "l"(zacc[fs][0]));
+                        asm("mov.b64 {%0, %1}, %2;" : "=f"(v.z), "=f"(v.w) : "l"(zacc[fs][1]));
                         *dst = epilogue(p.epilogue, v, old);
                     }
                 }
