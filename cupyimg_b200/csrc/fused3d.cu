@@ -218,6 +218,13 @@ fused3d_kernel(const __grid_constant__ FusedParams p, const __grid_constant__ CU
     const int oob_left = min(PITCH, max(0, HL - x0)), oob_right = min(PITCH, max(0, x0 + TX + HL - p.nx));
     const int need_bot = min(oob_bot, R), need_right = min(oob_right, HL);
     const bool patch_rows = (oob_top + oob_bot) > 0 && p.mode_y != SEPFILT_CONSTANT;
+    // Measured and rejected for the x edges (512^3, sigma 2, reflect; per-CTA cycle counters): letting the
+    // y-pass thread that produces a source column also store it to its mirror position in the y-filtered
+    // tile (no raw column cells, no patch team in x-edge tiles) — the extra dependent LDS/STS chain on
+    // the y-pass warps, which are the critical path of a phase, cost an x-edge CTA +21 % against +19 %
+    // for the table-driven patch below (0.337 -> 0.403 ms for the launch).  Also measured: TMA prefetch
+    // of the planes 2 / 4 / 8 groups ahead into L2 (cp.async.bulk.prefetch.tensor): no gain in constant
+    // mode, 0.336 -> 0.375 ms in reflect mode (the issuing thread belongs to the patch team).
     const bool patch_cols = (oob_left + oob_right) > 0 && p.mode_x != SEPFILT_CONSTANT;
     const bool patching = patch_rows || patch_cols;
     constexpr int NONE = -1;
@@ -498,7 +505,11 @@ fused3d_kernel(const __grid_constant__ FusedParams p, const __grid_constant__ CU
         if (tid == 0 && k + 3 < n_groups) { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); issue(k + 3); }
     }
 #ifdef SEPFILT_DEBUG_CYCLES
-    if (tid == 0 && blockIdx.x < 4096) g_dbg_cycles[blockIdx.x] = clock64() - t_start;
+    if (tid == 0 && blockIdx.x < 1024) {
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        g_dbg_cycles[blockIdx.x] = (clock64() - t_start) | ((long long)smid << 48);
+    }
 #endif
 }
 

@@ -14,6 +14,12 @@ torch.cuda.synchronize()
 buf = (ctypes.c_longlong * 4096)()
 _ffi.lib().sepfilt_debug_cycles(buf, 4096)
 allc = np.array(buf[:])
+smid = (allc[:148] >> 48).astype(int)
+allc[:148] &= (1 << 48) - 1
+order = np.argsort(-allc[:148])
+print("slowest CTAs (cycles/1000, blockIdx, smid):", [(int(allc[i] // 1000), int(i), int(smid[i])) for i in order[:24]])
+print("fastest CTAs (cycles/1000, blockIdx, smid):", [(int(allc[i] // 1000), int(i), int(smid[i])) for i in order[-8:]])
+print("distinct SMs used:", len(set(smid.tolist())))
 c = allc[:148].reshape(37, 4)     # [tile_y][tile_x]
 for name, off in (("y-warp wait", 1024), ("patch-warp TMA wait", 2048), ("patch work", 3072)):
     w = allc[off:off + 148].reshape(37, 4)
