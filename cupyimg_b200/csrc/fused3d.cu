@@ -42,6 +42,10 @@ struct FusedParams {
     int mode_z, mode_y, mode_x;
     float cval;
     int tiles_x, tiles_y, ty;   // ty = rows per tile (<= TYM)
+    int pad_;                   // keeps the tap arrays at 4 (mod 8) bytes, see the static_assert below
+    int yshift;                 // tile row t covers rows [t * ty - yshift, (t + 1) * ty - yshift): the rows a whole
+                                // number of tiles overshoots the array by are split between the first and the last
+                                // tile row — the two that pay for y-edge patching — instead of the last alone
     int box_rows;               // ty + 2R: height of the TMA box
     int zseg, nzseg;            // output planes per z segment, number of segments
     float wz[2 * MAXR + 1], wy[2 * MAXR + 1], wx[2 * MAXR + 1];   // taps at offsets -R..R
@@ -183,7 +187,7 @@ fused3d_kernel(const __grid_constant__ FusedParams p, const __grid_constant__ CU
     const int tile_x = b % p.tiles_x; b /= p.tiles_x;
     const int tile_y = b % p.tiles_y; b /= p.tiles_y;
     const int seg = b;
-    const int x0 = tile_x * TX, y0 = tile_y * p.ty;
+    const int x0 = tile_x * TX, y0 = tile_y * p.ty - p.yshift;   // y0 < 0 in the first tile row when yshift > 0
     const int ty = min(p.ty, p.ny - y0);
     const int zb = seg * p.zseg, ze = min(zb + p.zseg, p.nz_out);
     // input planes this CTA consumes, in input coordinates
@@ -217,6 +221,7 @@ fused3d_kernel(const __grid_constant__ FusedParams p, const __grid_constant__ CU
     const int oob_top = min(p.box_rows, max(0, R - y0)), oob_bot = min(p.box_rows, max(0, y0 + p.box_rows - R - p.ny));
     const int oob_left = min(PITCH, max(0, HL - x0)), oob_right = min(PITCH, max(0, x0 + TX + HL - p.nx));
     const int need_bot = min(oob_bot, R), need_right = min(oob_right, HL);
+    const int need_top = min(oob_top, R);                             // staged rows further above the array are never read
     const bool patch_rows = (oob_top + oob_bot) > 0 && p.mode_y != SEPFILT_CONSTANT;
     // Measured and rejected for the x edges (512^3, sigma 2, reflect; per-CTA cycle counters): letting the
     // y-pass thread that produces a source column also store it to its mirror position in the y-filtered
@@ -234,7 +239,7 @@ fused3d_kernel(const __grid_constant__ FusedParams p, const __grid_constant__ CU
     const int ncols = patch_cols ? oob_left + need_right : 0;          // out-of-array columns per staged row
     const int rows_used = p.box_rows - (oob_bot - need_bot);           // staged rows a stored voxel can read
     const int ncell = ncols * rows_used;                               // column cells per plane (<= C::MAXCELL)
-    const int nrow = patch_rows ? oob_top + need_bot : 0;              // out-of-array rows per plane
+    const int nrow = patch_rows ? need_top + need_bot : 0;             // out-of-array rows per plane
     int* pcell = meta;                                                 // [MAXCELL] dst | src << 16
     int* prow = meta + C::MAXCELL;                                     // [RROWS]   dst | src << 16 (row offsets)
     // ncell / nrow / rg0 / rg1 live in shared memory (pinfo), not in registers: the y and x+z passes are
@@ -269,7 +274,7 @@ fused3d_kernel(const __grid_constant__ FusedParams p, const __grid_constant__ CU
             pcell[i] = m;
         }
         for (int i = tid; i < nrow; i += NT) {
-            const int ry = i < oob_top ? i : p.box_rows - oob_bot + (i - oob_top);
+            const int ry = i < need_top ? oob_top - need_top + i : p.box_rows - oob_bot + (i - need_top);
             const int sy = staged_row(ry);
             prow[i] = sy == -1 ? NONE : ((ry * PITCH) | ((sy >= 0 ? sy * PITCH : 0xffff) << 16));
         }
@@ -393,9 +398,9 @@ fused3d_kernel(const __grid_constant__ FusedParams p, const __grid_constant__ CU
 #pragma unroll
     for (int j = 0; j < ZS; ++j) zacc[j][0] = zacc[j][1] = 0ull;
     const int cg_o = tid % CGW, row_o = tid / CGW;
-    const bool owner = row_o < ty && x0 + 4 * cg_o < p.nx;
+    const bool owner = row_o < ty && y0 + row_o >= 0 && x0 + 4 * cg_o < p.nx;
     // the output pointer of the NEXT finished plane, advanced by one plane per step (no 64-bit multiply per plane)
-    float* out_ptr = p.out + (size_t)zb * plane_elems + (size_t)(y0 + row_o) * p.nx + x0 + 4 * cg_o;
+    float* out_ptr = p.out + (size_t)zb * plane_elems + (size_t)max(y0 + row_o, 0) * p.nx + x0 + 4 * cg_o;
     constexpr int EPI_AHEAD = 8;
     float4 old_next = make_float4(0.f, 0.f, 0.f, 0.f);
     if (EPI && !HAS_Z && p.epilogue >= 2 && owner) old_next = __ldcg(reinterpret_cast<const float4*>(out_ptr));
@@ -513,13 +518,19 @@ fused3d_kernel(const __grid_constant__ FusedParams p, const __grid_constant__ CU
 #endif
 }
 
-int radius_bucket(int r)
+int radius_bucket(int r, bool has_z)
 {
-    // radius 16 (33 taps) is NOT fused: 33 z accumulators x 4 columns force 256-thread CTAs on 64-wide
-    // tiles (1.5x y-pass halo work, 2 warps per sub-partition) and measured 1.25 ms on 512^3 against
-    // 1.02 ms for three tiled passes
+    // With a z pass, radius > 8 is NOT fused: 33 z accumulators x 4 columns force 256-thread CTAs on
+    // 64-wide tiles (1.5x y-pass halo work, 2 warps per sub-partition) and measured 1.25 ms on 512^3
+    // against 1.02 ms for three tiled passes.  Without one (stacks of 2-D images) the kernel carries no
+    // z state and serves radius 12 and 16 with 2-plane groups.  (Tiled z pass + this kernel for the
+    // y / x part of a 3-D filter: 1.04 ms on 512^3 sigma 4, no better than three tiled passes.)
     static const int buckets[] = {1, 2, 3, 4, 6, 8};
     for (int b : buckets) if (r <= b) return b;
+    if (!has_z) {
+        if (r <= 12) return 12;
+        if (r <= 16) return 16;
+    }
     return -1;
 }
 
@@ -585,8 +596,8 @@ bool fused3d_supported(const FusedVolume& v, const F32Taps taps[3], bool gradmag
 {
     int r = 0;
     for (int a = 0; a < 3; ++a) r = taps[a].radius > r ? taps[a].radius : r;
-    (void)gradmag;   // gradient magnitude = one launch per axis with the square / sum / sqrt in the store
-    if (radius_bucket(r) < 0) return false;
+    const bool z_pass = !(taps[0].radius == 0 && taps[0].w[0] == 1.0f);
+    if (radius_bucket(r, z_pass || gradmag) < 0) return false;   // gradient magnitude: one launch per axis, epilogue variants exist up to radius 8
     if (v.nx % 4 != 0 || (reinterpret_cast<uintptr_t>(v.in) & 15) || (reinterpret_cast<uintptr_t>(v.out) & 15))
         return false;
     if (v.nx < 1 || v.ny < 1 || v.nz_in < 1 || v.nz_out < 1) return false;
@@ -634,6 +645,8 @@ double plan_tiles(const FusedVolume& v, int R, bool has_z, int tx, int slots, Fu
         p->tiles_x = tiles_x;
         p->ty = best_ty;
         p->tiles_y = (v.ny + best_ty - 1) / best_ty;
+        const int over = p->tiles_y * best_ty - v.ny;
+        p->yshift = p->tiles_y >= 2 ? over / 2 : 0;
         p->zseg = (v.nz_out + best_seg - 1) / best_seg;
         p->nzseg = (v.nz_out + p->zseg - 1) / p->zseg;
     }
@@ -674,13 +687,24 @@ cudaError_t launch_r(const FusedVolume& v, FusedParams& p, cudaStream_t s)
 
 }  // namespace
 
+// y + x only, radius 12 / 16: one configuration (128-wide tiles, 2-plane groups, no epilogue variants)
+template <int R>
+cudaError_t launch_wide_xy(const FusedVolume& v, FusedParams& p, cudaStream_t s)
+{
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    plan_tiles(v, R, false, 128, sms, &p);
+    return launch_e<R, false, Cfg<R, 128, 2, 1>, false>(p, s);
+}
+
 static cudaError_t launch_one(const FusedVolume& v, const F32Taps taps[3], int epilogue_mode, cudaStream_t s)
 {
     int r = 0;
     for (int a = 0; a < 3; ++a) r = taps[a].radius > r ? taps[a].radius : r;
-    const int R = radius_bucket(r);
-    if (R < 0) return cudaErrorInvalidValue;
     const bool has_z = !(taps[0].radius == 0 && taps[0].w[0] == 1.0f);
+    const int R = radius_bucket(r, has_z || epilogue_mode != 0);
+    if (R < 0) return cudaErrorInvalidValue;
 
     FusedParams p;
     p.in = v.in; p.out = v.out;
@@ -688,6 +712,7 @@ static cudaError_t launch_one(const FusedVolume& v, const F32Taps taps[3], int e
     p.mode_z = v.mode[0]; p.mode_y = v.mode[1]; p.mode_x = v.mode[2];
     p.cval = v.cval;
     p.epilogue = epilogue_mode;
+    p.pad_ = 0; p.yshift = 0;
     recentre(taps[0], R, p.wz);
     recentre(taps[1], R, p.wy);
     recentre(taps[2], R, p.wx);
@@ -705,6 +730,8 @@ static cudaError_t launch_one(const FusedVolume& v, const F32Taps taps[3], int e
     case 6 * 2 + 1: return launch_r<6, true>(v, p, s);
     case 8 * 2 + 0: return launch_r<8, false>(v, p, s);
     case 8 * 2 + 1: return launch_r<8, true>(v, p, s);
+    case 12 * 2 + 0: return launch_wide_xy<12>(v, p, s);
+    case 16 * 2 + 0: return launch_wide_xy<16>(v, p, s);
     default: return cudaErrorInvalidValue;
     }
 }
