@@ -434,5 +434,7 @@ def test_f32_radius_9_to_16(mode, ndi):
             want = oracle.gaussian_filter(x, sig(sigma), mode=mode)
             _ffi.LAUNCHES = 0
             got = to_host(ndi.gaussian_filter(xd, sig(sigma), mode=mode))
-            assert _ffi.LAUNCHES == launches, (shape, sigma, _ffi.LAUNCHES)
+            # wrap along y / x is declined by the fused kernel (far-side sources): per-axis passes
+            expect = len(shape) - (1 if launches == 1 else 0) if mode == "wrap" else launches
+            assert _ffi.LAUNCHES == expect, (shape, sigma, _ffi.LAUNCHES)
             assert_f32_close(got, want, atol_scale=2e-6)
