@@ -128,7 +128,7 @@ def make_pass(axis, taps, origin, mode_code, uniform=False, size=0):
     p.axis = int(axis)
     p.origin = int(origin)
     p.mode = int(mode_code)
-    p.uniform = 1 if uniform else 0
+    p.uniform = int(uniform)               # 0 taps, 1 mean, 2 minimum, 3 maximum
     keep = None
     if uniform:
         p.ntaps = int(size)

@@ -97,6 +97,7 @@ int check_pass(const sepfilt_pass* p, int ndim)
 // taps of one pass as offsets -R..R around the output position, rounded to f32
 bool pass_to_f32_taps(const sepfilt_pass* p, F32Taps* t)
 {
+    if (p->uniform > 1) return false;            // minimum / maximum windows are not correlations
     const int before = p->ntaps / 2 + p->origin;
     const int after = p->ntaps - 1 - before;
     const int R = before > after ? before : after;
@@ -249,7 +250,8 @@ int sepfilt_correlate1d(const sepfilt_tensor* in, const sepfilt_tensor* out,
     }
     p.ndim = nd;
     if (pass->uniform) {
-        p.symmetric = 2;
+        if (pass->uniform < 1 || pass->uniform > 3) return fail(SEPFILT_ERR_INVALID, "unknown window kind %d", pass->uniform);
+        p.symmetric = 1 + pass->uniform;         // 2: mean, 3: minimum, 4: maximum
     } else {
         p.symmetric = probe_symmetry(pass->taps, pass->ntaps);
         if (pass->ntaps <= SEPFILT_PARAM_TAPS) {

@@ -61,11 +61,20 @@ exact_corr1d_kernel(const __grid_constant__ ExactParams p)
             acc = __dmul_rn(il(size2), fw(size2));
             for (int j = -size1; j < size2; ++j)
                 acc = __dadd_rn(acc, __dmul_rn(il(j), fw(j)));
-        } else {
+        } else if (p.symmetric == 2) {
             // uniform_filter1d: exact window sum, one division
             acc = 0.0;
             for (int j = -size1; j <= size2; ++j) acc = __dadd_rn(acc, il(j));
             acc = __ddiv_rn(acc, (double)K);
+        } else {
+            // minimum_filter1d (3) / maximum_filter1d (4): the reference's generated kernel compares in
+            // double (filters.py:1511-1557, "value = min(cast<double>(x), value)"), C comparison semantics
+            acc = il(-size1);
+            if (p.symmetric == 3) {
+                for (int j = -size1 + 1; j <= size2; ++j) { const double v = il(j); acc = v < acc ? v : acc; }
+            } else {
+                for (int j = -size1 + 1; j <= size2; ++j) { const double v = il(j); acc = v > acc ? v : acc; }
+            }
         }
         store_cast(p.out + ooff, p.out_dtype, acc);
     }

@@ -85,10 +85,11 @@ __device__ __forceinline__ double pair_term(double a, double b)
 // column kernel
 // =====================================================================================
 // registers: the float64 window (2 per cell) + two raw row blocks + ~28 for addressing / accumulation
-// Measured on B200, 8 x 2048 x 2048, 9 taps (tools/time_c3.py): 2 columns per thread beat 4 (uint16:
-// 0.037 vs 0.056 ms — 96 registers and 5 CTAs / SM against 168 and 3), and the register double buffer
-// of the next block's rows pays only where the pass is HBM-bound (float64: 0.090 vs 0.113 ms, 91 % of
-// the measured copy bandwidth) — the 1- and 2-byte types are FP64-pipe bound and prefer the registers.
+// Measured on B200, 8 x 2048 x 2048, 9 taps (tools/time_c3.py, build-time variants of these two macros):
+// uint16 column pass 0.061 ms (2 columns, no register prefetch: 96 registers, 5 CTAs / SM), 0.061 (2, prefetch),
+// 0.058 (4 columns, none: 168 registers, 3 CTAs / SM), 0.062 (4, prefetch) — within 5 % of each other, the
+// FP64 pipe sits at 47 % in all of them; the register double buffer of the next block's rows pays where the
+// pass is HBM-bound (float64: 0.090 vs 0.113 ms, 91 % of the measured copy bandwidth).
 #ifndef STREAM_COLS
 #define STREAM_COLS 2
 #endif

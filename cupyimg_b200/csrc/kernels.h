@@ -21,7 +21,7 @@ struct ExactParams {
     int64_t     total;                   // number of output elements
     int32_t     K, before;               // before = K/2 + origin
     int32_t     mode;
-    int32_t     symmetric;               // +1 / -1 / 0 (scipy's probe), 2 = uniform window sum
+    int32_t     symmetric;               // +1 / -1 / 0 (scipy's probe), 2 = uniform window sum, 3 / 4 = window minimum / maximum
     double      cval;
     const double* wdev;                  // taps in device memory (K > SEPFILT_PARAM_TAPS) or nullptr
     double      w[SEPFILT_PARAM_TAPS];

@@ -9,6 +9,7 @@ Drop-in for the functions on the reference's separable hot path
     gaussian_filter1d :668    gaussian_filter :725    prewitt :828    sobel :889
     generic_laplace :963    laplace :1041    gaussian_laplace :1077
     generic_gradient_magnitude :1125    gaussian_gradient_magnitude :1207
+    minimum_filter / maximum_filter :1296-1396 (separable sizes)    minimum_filter1d / maximum_filter1d :1422-1508
 
 Inputs are CUDA arrays (``torch.Tensor``, ``cupy.ndarray`` or anything exposing
 ``__cuda_array_interface__`` / ``__dlpack__``); the result is the same kind of object.
@@ -40,6 +41,7 @@ __all__ = [
     "gaussian_filter1d", "gaussian_filter", "prewitt", "sobel",
     "generic_laplace", "laplace", "gaussian_laplace",
     "generic_gradient_magnitude", "gaussian_gradient_magnitude",
+    "minimum_filter1d", "maximum_filter1d", "minimum_filter", "maximum_filter",
 ]
 
 _F32 = np.dtype("float32")
@@ -176,7 +178,7 @@ class _PassSpec:
 
 
 def _f32_tiled_ok(src, dst, spec):
-    return (src.dtype == _F32 and dst.dtype == _F32 and src.c_contiguous() and dst.c_contiguous()
+    return (int(spec.uniform) <= 1 and src.dtype == _F32 and dst.dtype == _F32 and src.c_contiguous() and dst.c_contiguous()
             and spec.radius() <= _ffi.FAST_MAX_RADIUS)
 
 
@@ -216,6 +218,8 @@ def _fused_candidate(inp, out, specs, exact, gradmag=False):
     (sepfilt_separable_f32 answers SEPFILT_ERR_UNSUPPORTED and the caller falls back per axis)."""
     if exact or inp.dtype != _F32 or out.dtype != _F32 or inp.ndim not in (2, 3):
         return False
+    if any(int(s.uniform) > 1 for s in specs):
+        return False                    # minimum / maximum windows: exact per-axis passes
     if not (inp.c_contiguous() and out.c_contiguous()) or inp.size == 0 or inp.may_overlap(out):
         return False
     if len(specs) < 2 and not gradmag:
@@ -714,3 +718,92 @@ def gaussian_gradient_magnitude(input, sigma, output=None, mode="reflect", cval=
 
     return generic_gradient_magnitude(input, derivative, output, mode, cval,
                                       extra_arguments=(sigma,), extra_keywords=kwargs)
+
+
+# ----------------------------------------------------------------------------
+# minimum / maximum filters: the same per-axis skeleton with (min, max)
+# instead of (x, +)
+# ----------------------------------------------------------------------------
+_MIN, _MAX = 2, 3     # sepfilt_pass.uniform codes
+
+
+def _min_or_max_1d(input, size, axis, output, mode, cval, origin, kind):
+    """reference filters.py:1475-1508 (one generated kernel launch with a 1-D all-ones footprint)."""
+    inp = _ingest_input(input)
+    if inp.dtype.kind == "c":
+        raise TypeError("Complex type not supported")
+    size = int(size)
+    if size < 1:
+        raise RuntimeError("incorrect filter size")
+    axis = _normalize_axis_index(axis, inp.ndim)
+    origin = _check_origin(origin, size)
+    mode_code = _check_mode(mode)
+    _check_minmax_cval(cval)
+    out, _ = _get_output(output, inp)
+    _run_passes(inp, out, [_PassSpec(axis, None, origin, mode_code, uniform=kind, size=size)], cval, "ndimage")
+    return _array.export(out, inp)
+
+
+def _check_minmax_cval(cval):
+    if isinstance(cval, float) and cval != cval:
+        raise NotImplementedError("NaN cval is unsupported")         # filters.py:1382-1383
+
+
+def minimum_filter1d(input, size, axis=-1, output=None, mode="reflect", cval=0.0, origin=0):
+    """Minimum filter along one axis (reference filters.py:1422-1446)."""
+    return _min_or_max_1d(input, size, axis, output, mode, cval, origin, _MIN)
+
+
+def maximum_filter1d(input, size, axis=-1, output=None, mode="reflect", cval=0.0, origin=0):
+    """Maximum filter along one axis (reference filters.py:1449-1472)."""
+    return _min_or_max_1d(input, size, axis, output, mode, cval, origin, _MAX)
+
+
+def _min_or_max_filter(input, size, footprint, output, mode, cval, origin, kind, axes=None):
+    """reference filters.py:1373-1419: a size (or an all-True footprint, as in scipy) is separable and
+    runs as one 1-D pass per axis with size > 1 (_filters_core._run_1d_filters, _filters_core.py:79-109);
+    a general footprint needs the N-d kernel, which is outside this path."""
+    inp = _ingest_input(input)
+    if inp.dtype.kind == "c":
+        raise TypeError("Complex type not supported")
+    axes = _filter_axes(inp.ndim, axes)
+    if size is None and footprint is None:
+        raise RuntimeError("no footprint or filter size provided")
+    if footprint is not None:
+        fp = np.asarray(_array.host_weights(footprint) if _array.is_device_array(footprint) else footprint).astype(bool)
+        if fp.ndim != len(axes):
+            raise RuntimeError("footprint array has incorrect shape.")
+        if not fp.any():
+            raise ValueError("All-zero footprint is not supported.")
+        if not fp.all():
+            raise NotImplementedError("only separable minimum / maximum filters (a size or an all-True "
+                                      "footprint) are on this path")
+        sizes = list(fp.shape)
+    else:
+        sizes = [int(s) for s in _normalize_sequence(size, len(axes))]
+    _check_minmax_cval(cval)
+    origins = _normalize_sequence(origin, len(axes))
+    modes = _normalize_sequence(mode, len(axes))
+    out, _ = _get_output(output, inp)
+    specs = []
+    for a, sz, og, md in zip(axes, sizes, origins, modes):
+        if sz < 1:
+            raise RuntimeError("incorrect filter size")
+        mode_code = _check_mode(md)
+        og = _check_origin(og, sz)
+        if sz > 1:
+            specs.append(_PassSpec(a, None, og, mode_code, uniform=kind, size=sz))
+    _run_passes(inp, out, specs, cval, "ndimage")
+    return _array.export(out, inp)
+
+
+def minimum_filter(input, size=None, footprint=None, output=None, mode="reflect", cval=0.0, origin=0, *,
+                   axes=None):
+    """Multi-dimensional minimum filter (reference filters.py:1296-1332), separable case."""
+    return _min_or_max_filter(input, size, footprint, output, mode, cval, origin, _MIN, axes)
+
+
+def maximum_filter(input, size=None, footprint=None, output=None, mode="reflect", cval=0.0, origin=0, *,
+                   axes=None):
+    """Multi-dimensional maximum filter (reference filters.py:1335-1370), separable case."""
+    return _min_or_max_filter(input, size, footprint, output, mode, cval, origin, _MAX, axes)

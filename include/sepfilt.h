@@ -97,7 +97,8 @@ typedef struct {
     const double* taps;      /* HOST pointer, K correlation weights */
     int32_t       origin;    /* -(K/2) <= origin <= (K-1)/2   (_util.py:98-102) */
     int32_t       mode;      /* sepfilt_mode */
-    int32_t       uniform;   /* 1: scipy uniform_filter1d semantics (window sum / K); taps ignored */
+    int32_t       uniform;   /* window filters, taps ignored: 1 = scipy uniform_filter1d semantics (window sum / K);
+                              * 2 = minimum_filter1d, 3 = maximum_filter1d (filters.py:1422-1557), exact path only */
     int32_t       reserved;
 } sepfilt_pass;
 

@@ -398,3 +398,70 @@ def gaussian_laplace(input, sigma, output=None, mode="reflect", cval=0.0, **kwar
 
     return generic_laplace(input, derivative2, output, mode, cval,
                            extra_arguments=(sigma,), extra_keywords=kwargs)
+
+
+# ---- minimum / maximum filters ---------------------------------------
+def _min_or_max_1d(input, size, axis, output, mode, cval, origin, func):
+    """The reference's generated min / max kernel with a 1-D all-ones footprint (filters.py:1475-1557):
+    the window [i - size//2 - origin, ... + size) through the boundary rule (_util.py:170-228), compared
+    as double ("value = min(cast<double>(x), value)"), stored with the C cast."""
+    input = np.asarray(input)
+    size = int(size)
+    if size < 1:
+        raise RuntimeError("incorrect filter size")
+    axis = _axis(axis, input.ndim)
+    if size // 2 + origin < 0 or size // 2 + origin >= size:
+        raise ValueError("invalid origin")
+    if mode not in MODES:
+        raise RuntimeError("boundary mode not supported")
+    output = _get_output(output, input)
+    if input.size == 0:
+        return output
+    n = input.shape[axis]
+    x = np.moveaxis(input.astype(np.float64), axis, -1)
+    ext = np.concatenate([x, np.full(x.shape[:-1] + (1,), float(cval))], axis=-1)   # index n = cval
+    idx = np.empty((n, size), np.int64)
+    for i in range(n):
+        for k in range(size):
+            m = remap(mode, i - size // 2 - origin + k, n)
+            idx[i, k] = n if m < 0 else m
+    win = ext[..., idx]                                                           # (..., n, size)
+    red = win.min(axis=-1) if func == "min" else win.max(axis=-1)
+    red = np.ascontiguousarray(np.moveaxis(red, -1, axis))
+    res = np.empty(input.shape, output.dtype)
+    lib().oracle_copy_cast(red.ctypes.data, _DT[np.dtype(np.float64)], res.ctypes.data, _DT[res.dtype], red.size)
+    output[...] = res
+    return output
+
+
+def minimum_filter1d(input, size, axis=-1, output=None, mode="reflect", cval=0.0, origin=0):
+    return _min_or_max_1d(input, size, axis, output, mode, cval, origin, "min")
+
+
+def maximum_filter1d(input, size, axis=-1, output=None, mode="reflect", cval=0.0, origin=0):
+    return _min_or_max_1d(input, size, axis, output, mode, cval, origin, "max")
+
+
+def _min_or_max_filter(input, size, output, mode, cval, origin, func):
+    """Separable case of filters.py:1373-1419 through _filters_core._run_1d_filters (:79-109): one 1-D
+    pass per axis with size > 1, every pass stored in the output dtype."""
+    input = np.asarray(input)
+    output = _get_output(output, input)
+    sizes, origins, modes = (_seq(v, input.ndim) for v in (size, origin, mode))
+    axes = [a for a in range(input.ndim) if sizes[a] > 1]
+    if not axes:
+        lib().oracle_copy_cast(np.ascontiguousarray(input).ctypes.data, _DT[input.dtype],
+                               output.ctypes.data, _DT[output.dtype], input.size)
+        return output
+    for a in axes:
+        _min_or_max_1d(input, int(sizes[a]), a, output, modes[a], cval, origins[a], func)
+        input = output.copy()
+    return output
+
+
+def minimum_filter(input, size=3, output=None, mode="reflect", cval=0.0, origin=0):
+    return _min_or_max_filter(input, size, output, mode, cval, origin, "min")
+
+
+def maximum_filter(input, size=3, output=None, mode="reflect", cval=0.0, origin=0):
+    return _min_or_max_filter(input, size, output, mode, cval, origin, "max")

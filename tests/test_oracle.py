@@ -154,3 +154,43 @@ def test_complex_oracle_matches_scipy():
         oracle.correlate1d(np.ones(4, np.complex64), [1.0, 2.0], output=np.float64)
     with pytest.raises(ValueError):
         oracle.correlate1d(np.ones(4), np.array([1.0, 2.0j]), cval=1j, mode="constant")
+
+
+# the reference's literal known answers for the separable min / max filters
+# (tests/test_ndimage.py:754-795 minimum_filter01-06, :830-873 maximum_filter01-06)
+MINMAX_KATS = [
+    ("minimum_filter", [1, 2, 3, 4, 5], [2], [1, 1, 2, 3, 4]),
+    ("minimum_filter", [1, 2, 3, 4, 5], [3], [1, 1, 2, 3, 4]),
+    ("minimum_filter", [3, 2, 5, 1, 4], [2], [3, 2, 2, 1, 1]),
+    ("minimum_filter", [3, 2, 5, 1, 4], [3], [2, 2, 1, 1, 1]),
+    ("minimum_filter", [[3, 2, 5, 1, 4], [7, 6, 9, 3, 5], [5, 8, 3, 7, 1]], [2, 3],
+     [[2, 2, 1, 1, 1], [2, 2, 1, 1, 1], [5, 3, 3, 1, 1]]),
+    ("maximum_filter", [1, 2, 3, 4, 5], [2], [1, 2, 3, 4, 5]),
+    ("maximum_filter", [1, 2, 3, 4, 5], [3], [2, 3, 4, 5, 5]),
+    ("maximum_filter", [3, 2, 5, 1, 4], [2], [3, 3, 5, 5, 4]),
+    ("maximum_filter", [3, 2, 5, 1, 4], [3], [3, 5, 5, 5, 4]),
+    ("maximum_filter", [[3, 2, 5, 1, 4], [7, 6, 9, 3, 5], [5, 8, 3, 7, 1]], [2, 3],
+     [[3, 5, 5, 5, 4], [7, 9, 9, 9, 5], [8, 9, 9, 9, 7]]),
+]
+
+
+def test_minmax_oracle_known_answers_and_scipy():
+    """minimum / maximum filters.  Reference known answers, then scipy bit for bit
+    over dtype x mode x size x origin x axis (the oracle follows the reference's kernel: compare as
+    double, C-cast store)."""
+    for fn, x, size, want in MINMAX_KATS:
+        np.testing.assert_array_equal(getattr(oracle, fn)(np.asarray(x), size), np.asarray(want))
+    rng = np.random.default_rng(0)
+    for dt in ["uint8", "int16", "uint16", "int64", "float32", "float64"]:
+        x = (rng.random((4, 9, 6)) * 200 - (0 if dt[0] == "u" else 50)).astype(dt)
+        for mode, size, fn in itertools.product(["reflect", "constant", "nearest", "mirror", "wrap"],
+                                                [1, 2, 3, 7, 12], ["minimum", "maximum"]):
+            for origin in sorted({-(size // 2), 0, (size - 1) // 2}):
+                for axis in (0, 1, 2):
+                    got = getattr(oracle, fn + "_filter1d")(x, size, axis=axis, mode=mode, cval=3.0, origin=origin)
+                    want = getattr(sndi, fn + "_filter1d")(x, size, axis=axis, mode=mode, cval=3.0, origin=origin)
+                    assert got.dtype == want.dtype
+                    np.testing.assert_array_equal(got, want)
+            got = getattr(oracle, fn + "_filter")(x, size=[size, 1, 3], mode=mode, cval=-2.0, output=np.float32)
+            want = getattr(sndi, fn + "_filter")(x, size=[size, 1, 3], mode=mode, cval=-2.0, output=np.float32)
+            np.testing.assert_array_equal(got, want)
