@@ -257,7 +257,7 @@ def run_ours(args):
             hy.copy_(out, non_blocking=True)
         else:
             # the public host-volume API: z-chunks streamed H2D -> filter -> D2H on three streams
-            host_api.gaussian_filter_host(hx, SIGMA, output=hy, mode=MODE, truncate=TRUNCATE, chunk_planes=64)
+            host_api.gaussian_filter_host(hx, SIGMA, output=hy, mode=MODE, truncate=TRUNCATE, chunk_planes=32)
 
     e2e_step()
     barrier()
@@ -297,12 +297,11 @@ def run_ours(args):
                        "sharding": "none" if world == 1 else "z-slabs, 8-plane halo exchange over NCCL send/recv",
                        "l2": "input 512 MiB + output 512 MiB per step, both larger than the 126 MB L2; no flush"},
             "roofline": roofline, "e2e": {"value": e2e_value, "unit": UNIT,
-                                           "h2d_bytes_per_step": (NZ + (2 * 8 * (NZ // 64 - 1) if world == 1 else 0))
-                                                                 * NY * NX * 4 * world,
+                                           "h2d_bytes_per_step": NZ * NY * NX * 4 * world,
                                            "d2h_bytes_per_step": NZ * NY * NX * 4 * world,
                                            "steps": e2e_steps,
                                            "api": "cupyimg_b200.host.gaussian_filter_host (pinned host in / out, "
-                                                  "64-plane chunks + 8-plane halos, 3 streams)" if world == 1 else
+                                                  "32-plane chunks, halos filled device-to-device, 3 streams)" if world == 1 else
                                                   "pinned H2D copy + sharded.ZSlabFilter.gaussian_filter + D2H copy"},
             "gpu_launches": launches, "clocks": clocks,
         }

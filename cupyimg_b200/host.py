@@ -3,10 +3,11 @@
 A caller of the reference moves a volume to the device (``cupy.asarray``), filters it and moves
 the result back (``cupy.asnumpy``): three serial steps, with the PCIe transfers dominating.  For
 volumes that live in host memory this module pipelines the same work: the volume is cut into
-z-chunks, each chunk (plus the r halo planes the z pass needs, taken straight from the host
-array) is copied to the device on one stream, filtered on a second stream through the windowed
-C-ABI call (``in_offset0``: halo planes are read, never written) and copied back on a third, with
-three chunks in flight.  H2D and D2H run concurrently (full-duplex PCIe) and hide the kernels.
+z-chunks, each chunk is copied to the device on one stream — every plane crosses PCIe exactly once:
+the r halo planes the z pass needs are filled device-to-device from the neighbouring chunk buffers —
+filtered on a second stream through the windowed C-ABI call (``in_offset0``: halo planes are read,
+never written) and copied back on a third, with four chunks in flight.  H2D and D2H run concurrently
+(full-duplex PCIe) and hide the kernels.
 
 The result is bit-identical to filtering the whole volume at once: a chunk's window never touches
 the ends of its device buffer except where those are the ends of the volume, so the boundary rule
@@ -40,7 +41,12 @@ def _run_chunked(x, out, specs, cval, dtype_mode, chunk_planes, device):
         out.copy_(o)
         return out
     C = int(chunk_planes)
-    NB = 3
+    if C < 2 * r:
+        C = 2 * r                                            # a chunk must hold its neighbours' halos
+    NB = 4
+    # device chunk buffers laid out [r lower halo | C own planes | r upper halo].  Every plane crosses
+    # PCIe exactly once: the halos are filled device-to-device from the neighbouring chunk buffers, so a
+    # chunk is filtered one chunk late, when its successor has landed.
     ibuf = [torch.empty((C + 2 * r, ny, nx), dtype=x.dtype, device=dev) for _ in range(NB)]
     obuf = [torch.empty((C, ny, nx), dtype=x.dtype, device=dev) for _ in range(NB)]
     s_in, s_run, s_out = (torch.cuda.Stream(dev) for _ in range(3))
@@ -50,22 +56,43 @@ def _run_chunked(x, out, specs, cval, dtype_mode, chunk_planes, device):
     for s in (s_in, s_run, s_out):
         s.wait_event(start)
     chunks = [(z0, min(z0 + C, nz)) for z0 in range(0, nz, C)]
-    for i, (z0, z1) in enumerate(chunks):
-        lo, hi = max(z0 - r, 0), min(z1 + r, nz)
-        b = i % NB
+    if len(chunks) > 1 and chunks[-1][1] - chunks[-1][0] < r:
+        # a last chunk thinner than the halo cannot serve its predecessor: merge it
+        chunks[-2:] = [(chunks[-2][0], nz)]
+        grow = chunks[-1][1] - chunks[-1][0] - C
+        ibuf = [torch.empty((C + grow + 2 * r, ny, nx), dtype=x.dtype, device=dev) for _ in range(NB)]
+        obuf = [torch.empty((C + grow, ny, nx), dtype=x.dtype, device=dev) for _ in range(NB)]
+    n = len(chunks)
+
+    def load(i):
+        z0, z1 = chunks[i]
         with torch.cuda.stream(s_in):
             if i >= NB:
-                s_in.wait_event(ev_run[i - NB])                 # the kernel that read this buffer is done
-            src = ibuf[b][:hi - lo]
-            src.copy_(x[lo:hi], non_blocking=True)
+                s_in.wait_event(ev_run[i - NB + 1])             # this buffer's chunk AND its successor are filtered
+            ibuf[i % NB][r:r + (z1 - z0)].copy_(x[z0:z1], non_blocking=True)
             ev_in[i] = torch.cuda.Event()
             ev_in[i].record(s_in)
+
+    def run(i):
+        z0, z1 = chunks[i]
+        b, m = i % NB, z1 - z0
         with torch.cuda.stream(s_run):
-            s_run.wait_event(ev_in[i])
+            s_run.wait_event(ev_in[min(i + 1, n - 1)])          # own planes and the successor's have landed
+            buf = ibuf[b]
+            lo = 0
+            if i > 0:
+                pz0, pz1 = chunks[i - 1]
+                buf[:r].copy_(ibuf[(i - 1) % NB][r + (pz1 - pz0) - r:r + (pz1 - pz0)], non_blocking=True)
+            else:
+                lo = r
+            hi = r + m
+            if i + 1 < n:
+                buf[r + m:r + m + r].copy_(ibuf[(i + 1) % NB][r:2 * r], non_blocking=True)
+                hi = r + m + r
             if i >= NB:
-                s_run.wait_event(ev_out[i - NB])                # the copy that drained this buffer is done
-            dst = obuf[b][:z1 - z0]
-            _filters._run_passes_window(_array.ingest(src), _array.ingest(dst), specs, cval, dtype_mode, z0 - lo)
+                s_run.wait_event(ev_out[i - NB])                # the copy that drained this output buffer is done
+            dst = obuf[b][:m]
+            _filters._run_passes_window(_array.ingest(buf[lo:hi]), _array.ingest(dst), specs, cval, dtype_mode, r - lo)
             ev_run[i] = torch.cuda.Event()
             ev_run[i].record(s_run)
         with torch.cuda.stream(s_out):
@@ -73,6 +100,12 @@ def _run_chunked(x, out, specs, cval, dtype_mode, chunk_planes, device):
             out[z0:z1].copy_(dst, non_blocking=True)
             ev_out[i] = torch.cuda.Event()
             ev_out[i].record(s_out)
+
+    for i in range(n):
+        load(i)
+        if i >= 1:
+            run(i - 1)
+    run(n - 1)
     done = torch.cuda.Event()
     done.record(s_out)
     torch.cuda.current_stream(dev).wait_event(done)
@@ -82,7 +115,7 @@ def _run_chunked(x, out, specs, cval, dtype_mode, chunk_planes, device):
 
 
 def gaussian_filter_host(input, sigma, order=0, output=None, mode="reflect", cval=0.0, truncate=4.0, *,
-                         chunk_planes=64, device=None, dtype_mode=None):
+                         chunk_planes=32, device=None, dtype_mode=None):
     """``gaussian_filter`` for a 3-D CPU tensor, streamed through the GPU in z-chunks.
     Returns a CPU tensor (``output`` or a new pinned one).  The call returns once the work is
     enqueued on the current stream; synchronise that stream before reading the result."""
@@ -96,7 +129,7 @@ def gaussian_filter_host(input, sigma, order=0, output=None, mode="reflect", cva
 
 
 def uniform_filter_host(input, size=3, output=None, mode="reflect", cval=0.0, origin=0, *,
-                        chunk_planes=64, device=None, dtype_mode=None):
+                        chunk_planes=32, device=None, dtype_mode=None):
     """``uniform_filter`` for a 3-D CPU tensor, streamed through the GPU in z-chunks."""
     x = input
     if output is None:
