@@ -418,6 +418,13 @@ def test_host_pipeline_matches_resident_filter(ndi):
     got = host.gaussian_filter_host(xi, 1.5, chunk_planes=32)
     torch.cuda.synchronize()
     assert torch.equal(got, want)
+    # chunk edge cases: a last chunk thinner than the halo (150 = 4 x 36 + 6, radius 8: merged into its
+    # predecessor), chunks smaller than two halos (raised to 2 r), more chunks than chunk buffers
+    want = ndi.gaussian_filter(x.cuda(), 2.0).cpu()
+    for c in (36, 8, 16, 20, 149, 150, 400):
+        got = host.gaussian_filter_host(x, 2.0, chunk_planes=c)
+        torch.cuda.synchronize()
+        assert torch.equal(got, want), c
 
 
 @pytest.mark.parametrize("mode", ["reflect", "constant", "nearest", "mirror", "wrap"])
