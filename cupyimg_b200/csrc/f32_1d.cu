@@ -14,6 +14,7 @@
 // parameters (constant bank), zero-padded to the compile-time radius bucket R.
 // These replace one `_call_kernel` launch (_filters_core.py:152) each; the fused
 // multi-axis kernel in fused3d.cu replaces a whole per-axis loop.
+#include <cstdlib>
 #include "common.cuh"
 #include "kernels.h"
 
@@ -238,6 +239,8 @@ static cudaError_t launch_bucket(const F32Line& g, const F32Taps& t, cudaStream_
 
 cudaError_t launch_f32_corr1d(const F32Line& g, const F32Taps& t, cudaStream_t s)
 {
+    static const bool no_stream = getenv("SEPFILT_NO_F32_STREAM") != nullptr;   // A/B aid
+    if (!no_stream && f32_stream_supported(g, t.radius)) return launch_f32_stream(g, t, s);
     switch (radius_bucket(t.radius)) {
     case 1: return launch_bucket<1>(g, t, s);
     case 2: return launch_bucket<2>(g, t, s);

@@ -1,0 +1,297 @@
+// f32_stream.cu — register-streaming single-axis float32 passes (float32 in, float32 FMA accumulate,
+// float32 out): correlate1d / convolve1d / gaussian_filter1d on float32 arrays, the per-axis passes of
+// 3-D filters the fused kernel declines (radius > 8 with a z pass, wrap along y / x, cval != 0).
+// Same arithmetic contract as f32_1d.cu (rtol 1e-5 of scipy); what changes is the data movement — no
+// shared memory, no CTA barrier, every element loaded from DRAM once:
+//   f32_stream_col_kernel  filtered axis strided: a thread owns C adjacent columns (one 8- or 16-byte
+//       load per row) and marches a segment of the axis; every input row is scattered at once into 2R+1
+//       per-column accumulators that shift by one output per step.  The loop is unrolled by 2R+1 so the
+//       accumulator of logical index j at step s is physical slot (j + s) mod (2R+1): in-place updates, no
+//       register moves.  The rows of the next P steps are in flight in a register ring (slot reloaded right
+//       after it is consumed).  Segments are sized to whole waves of the resident CTAs.
+//   f32_stream_row_kernel  contiguous axis: a thread loads the two 16-byte chunks of its 8 outputs plus the
+//       halo chunks on either side straight from global memory (its neighbours' chunks: L1 hits) and stores
+//       two 16-byte vectors; chunks that are not fully inside the row are gathered element-wise through the
+//       boundary rule (_util.py:170-228), which only the edge threads of a row do.
+// Geometries these kernels do not take (unaligned pointers, inner extents that are not a multiple of the
+// column vector) stay on the shared-memory tiles of f32_1d.cu.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace sepfilt {
+
+namespace {
+
+struct FStreamParams {
+    const float* in;
+    float*       out;
+    int64_t      outer, inner;
+    int32_t      n_in, n_out;
+    int32_t      shift;               // source index of the filter centre = output position + shift
+    int32_t      mode;
+    int32_t      seg;                 // col kernel: output rows per segment
+    int32_t      xblocks;             // col kernel: CTAs across `inner`
+    int32_t      gpr;                 // row kernel: 8-output groups per row
+    int32_t      row_aligned;         // row kernel: every row start is 16-byte aligned (in and out)
+    float        cval;
+    float        w[2 * SEPFILT_FAST_MAX_RADIUS + 1];   // taps at offsets -R..R
+};
+
+__device__ __noinline__ int fremap_outside(int mode, int ix, int n) { return remap_index32(mode, ix, n); }
+__device__ __forceinline__ int fremap_fast(int mode, int ix, int n)
+{
+    if ((unsigned)ix < (unsigned)n) return ix;
+    if (mode == SEPFILT_CONSTANT) return -1;
+    if (mode == SEPFILT_NEAREST) return ix < 0 ? 0 : n - 1;
+    if (ix > -n && ix < 2 * n - 1) {
+        const bool low = ix < 0;
+        if (mode == SEPFILT_REFLECT) return low ? -1 - ix : 2 * n - 1 - ix;
+        if (mode == SEPFILT_MIRROR) return low ? -ix : 2 * n - 2 - ix;
+        return low ? ix + n : ix - n;
+    }
+    return fremap_outside(mode, ix, n);
+}
+
+template <int C> struct alignas(4 * C) FPack { float v[C]; };
+
+// ---- column kernel geometry: columns per thread, prefetch ring (a divisor of 2R+1) ----
+template <int R> struct FColGeom {
+    static constexpr int W = 2 * R + 1;
+    static constexpr int C = R <= 4 ? 4 : 2;
+    static constexpr int ring()
+    {
+        int best = 1;
+        for (int p = 1; p <= W; ++p)
+            if (W % p == 0 && p * C <= 52) best = p;          // largest divisor of W within the register budget
+        return best;
+    }
+    static constexpr int P = ring();
+    static constexpr int REGS = W * C + P * C + 48;
+    static constexpr int CTAS = REGS <= 76 ? 6 : (REGS <= 92 ? 5 : (REGS <= 120 ? 4 : 3));
+};
+
+template <int R>
+__global__ void __launch_bounds__(128, (FColGeom<R>::CTAS))
+f32_stream_col_kernel(const __grid_constant__ FStreamParams p)
+{
+    typedef FColGeom<R> G;
+    constexpr int W = G::W, C = G::C, P = G::P;
+    typedef FPack<C> V;
+    const int64_t bx = blockIdx.x;
+    const int64_t o = bx / p.xblocks;
+    const int64_t col = ((bx - o * p.xblocks) * 128 + threadIdx.x) * C;
+    if (col >= p.inner) return;
+    const int p0 = blockIdx.y * p.seg;
+    const int p_end = min(p0 + p.seg, p.n_out);
+    const float* __restrict__ in = p.in + o * (int64_t)p.n_in * p.inner + col;
+    float* __restrict__ out = p.out + o * (int64_t)p.n_out * p.inner + col;
+    // input rows q0 .. q0 + (p_end - p0) + 2R - 1 are consumed in order; the output finished by input
+    // row q is p = q - shift - R
+    const int q0 = p0 + p.shift - R;
+    const int n_steps = (p_end - p0) + 2 * R;
+
+    auto fetch = [&](int q) -> V {                           // one row of this thread's columns (uniform remap)
+        V v;
+        const int m = fremap_fast(p.mode, q, p.n_in);
+        if (m < 0) {
+#pragma unroll
+            for (int c = 0; c < C; ++c) v.v[c] = p.cval;
+        } else {
+            v = *reinterpret_cast<const V*>(in + (int64_t)m * p.inner);
+        }
+        return v;
+    };
+    V pre[P];
+#pragma unroll
+    for (int i = 0; i < P; ++i) pre[i] = fetch(q0 + i);
+    float acc[W][C];
+#pragma unroll
+    for (int j = 0; j < W; ++j)
+#pragma unroll
+        for (int c = 0; c < C; ++c) acc[j][c] = 0.f;
+
+    for (int base = 0; base < n_steps; base += W) {
+        const bool interior = q0 + base >= 0 && q0 + base + W + P <= p.n_in && base + W <= n_steps;
+#pragma unroll
+        for (int s = 0; s < W; ++s) {
+            const int t = base + s;
+            if (!interior && t >= n_steps) break;
+            const V v = pre[s % P];
+            // slot reloaded right after it is consumed: prefetch distance P rows
+            if (interior) pre[s % P] = *reinterpret_cast<const V*>(in + (int64_t)(q0 + t + P) * p.inner);
+            else if (t + P < n_steps) pre[s % P] = fetch(q0 + t + P);
+            // logical accumulator j lives in slot (j + s) % W at step s of a block (in place, no moves)
+#pragma unroll
+            for (int j = 0; j < 2 * R; ++j)
+#pragma unroll
+                for (int c = 0; c < C; ++c)
+                    acc[(j + 1 + s) % W][c] = fmaf(v.v[c], p.w[2 * R - j], acc[(j + 1 + s) % W][c]);
+#pragma unroll
+            for (int c = 0; c < C; ++c) acc[s % W][c] = v.v[c] * p.w[0];
+            if (t >= 2 * R) {                                // logical accumulator 0 of the NEXT step is complete
+                V r;
+#pragma unroll
+                for (int c = 0; c < C; ++c) r.v[c] = acc[(s + 1) % W][c];
+                *reinterpret_cast<V*>(out + (int64_t)(p0 + t - 2 * R) * p.inner) = r;
+            }
+        }
+    }
+}
+
+// ---- row kernel ----
+constexpr int FROW_P = 8;            // outputs per thread
+constexpr int FROW_THREADS = 128;
+
+template <int R>
+__global__ void __launch_bounds__(FROW_THREADS)
+f32_stream_row_kernel(const __grid_constant__ FStreamParams p)
+{
+    constexpr int H = (R + 3) / 4;                           // halo chunks per side
+    constexpr int NW = FROW_P / 4 + 2 * H;                   // chunks in the window
+    constexpr int OFF = 4 * H - R;                           // window index of the leftmost tap of output 0
+    const int64_t gid = (int64_t)blockIdx.x * FROW_THREADS + threadIdx.x;
+    const int64_t row = gid / p.gpr;
+    if (row >= p.outer) return;
+    const int x = (int)(gid - row * p.gpr) * FROW_P;
+    const float* __restrict__ src = p.in + row * p.n_in;
+    const int g0 = x + p.shift - 4 * H;                      // source index of win[0]
+    const bool vec_ok = p.row_aligned && (p.shift & 3) == 0;
+    float win[4 * NW];
+#pragma unroll
+    for (int j = 0; j < NW; ++j) {
+        const int g = g0 + 4 * j;
+        if (vec_ok && g >= 0 && g + 4 <= p.n_in) {
+            const float4 v = *reinterpret_cast<const float4*>(src + g);
+            win[4 * j] = v.x; win[4 * j + 1] = v.y; win[4 * j + 2] = v.z; win[4 * j + 3] = v.w;
+        } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int m = fremap_fast(p.mode, g + e, p.n_in);
+                win[4 * j + e] = m < 0 ? p.cval : src[m];
+            }
+        }
+    }
+    float acc[FROW_P];
+#pragma unroll
+    for (int o = 0; o < FROW_P; ++o) acc[o] = win[OFF + o] * p.w[0];
+#pragma unroll
+    for (int k = 1; k <= 2 * R; ++k) {
+        const float w = p.w[k];
+#pragma unroll
+        for (int o = 0; o < FROW_P; ++o) acc[o] = fmaf(w, win[OFF + o + k], acc[o]);
+    }
+    float* __restrict__ dst = p.out + row * p.n_out + x;
+    if (p.row_aligned && x + FROW_P <= p.n_out) {
+        *reinterpret_cast<float4*>(dst) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        *reinterpret_cast<float4*>(dst + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+    } else {
+#pragma unroll
+        for (int o = 0; o < FROW_P; ++o)
+            if (x + o < p.n_out) dst[o] = acc[o];
+    }
+}
+
+int fstream_bucket(int r)
+{
+    static const int buckets[] = {1, 2, 3, 4, 6, 8, 12, 16};
+    for (int b : buckets) if (r <= b) return b;
+    return -1;
+}
+
+int fcols(int R) { return R <= 4 ? 4 : 2; }
+
+template <int R>
+cudaError_t launch_fstream(FStreamParams& p, const F32Taps& t, cudaStream_t s)
+{
+    for (int k = 0; k <= 2 * SEPFILT_FAST_MAX_RADIUS; ++k) p.w[k] = 0.f;
+    for (int k = 0; k <= 2 * t.radius; ++k) p.w[k + R - t.radius] = t.w[k];
+    if (p.inner == 1) {
+        const int64_t groups = p.outer * p.gpr;
+        f32_stream_row_kernel<R><<<(unsigned)((groups + FROW_THREADS - 1) / FROW_THREADS), FROW_THREADS, 0, s>>>(p);
+        return cudaGetLastError();
+    }
+    static const int per_sm = [] {
+        int n = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, f32_stream_col_kernel<R>, 128, 0) != cudaSuccess || n < 1)
+            n = FColGeom<R>::CTAS;
+        return n;
+    }();
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    // segment length: whole waves of the resident CTA slots, least halo re-reading (2R rows per segment)
+    const int64_t slots = (int64_t)sms * per_sm, cols = p.outer * p.xblocks;
+    double best = 1e300;
+    int best_seg = p.n_out;
+    for (int seg = 8; ; seg += 8) {
+        const int sg = seg < p.n_out ? seg : p.n_out;
+        const int64_t nseg = (p.n_out + sg - 1) / sg;
+        const int64_t waves = (cols * nseg + slots - 1) / slots;
+        const double cost = (double)waves * (sg + 2 * R + 8);
+        if (cost < best) { best = cost; best_seg = sg; }
+        if (seg >= p.n_out || seg >= 4096) break;
+    }
+    p.seg = best_seg;
+    if ((p.n_out + p.seg - 1) / p.seg > 65535) p.seg = (int32_t)((p.n_out + 65534) / 65535);
+    dim3 grid((unsigned)cols, (unsigned)((p.n_out + p.seg - 1) / p.seg));
+    f32_stream_col_kernel<R><<<grid, 128, 0, s>>>(p);
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+bool f32_stream_supported(const F32Line& g, int radius)
+{
+    const int R = fstream_bucket(radius);
+    if (R < 0) return false;
+    // Measured on 512^3 (tools/time_f32_1d.py, ms, streaming vs shared-memory tile): 5 taps 0.16-0.17 vs
+    // 0.23-0.25 (95-101 % of the measured copy bandwidth), 9 taps 0.19-0.20 vs 0.24-0.25, 17 taps column
+    // 0.252 vs 0.27 but row 0.352 vs 0.296 (every warp of a 512-wide row holds an edge thread whose
+    // element-wise halo gather grows with the radius), 25 / 33 taps 0.34-0.67 vs 0.30-0.35.
+    if (g.inner == 1 ? R > 4 : R > 8) return false;
+    if (g.n_in <= 0 || g.n_out <= 0 || g.outer <= 0 || g.inner <= 0) return false;
+    const uintptr_t a = reinterpret_cast<uintptr_t>(g.in) | reinterpret_cast<uintptr_t>(g.out);
+    if (g.inner == 1) {
+        if (a & 3) return false;
+        const int64_t groups = g.outer * ((g.n_out + FROW_P - 1) / FROW_P);
+        if ((groups + FROW_THREADS - 1) / FROW_THREADS > 2147483647LL) return false;
+    } else {
+        const int C = fcols(R);
+        if (g.inner % C != 0 || (a & (uintptr_t)(4 * C - 1))) return false;
+        if (g.outer * ((g.inner / C + 127) / 128) > 2147483647LL) return false;
+    }
+    return true;
+}
+
+cudaError_t launch_f32_stream(const F32Line& g, const F32Taps& t, cudaStream_t s)
+{
+    FStreamParams p;
+    p.in = g.in; p.out = g.out;
+    p.outer = g.outer; p.inner = g.inner;
+    p.n_in = g.n_in; p.n_out = g.n_out;
+    p.shift = g.in_offset;
+    p.mode = g.mode;
+    p.cval = g.cval;
+    p.seg = 0; p.xblocks = 0; p.gpr = 0; p.row_aligned = 0;
+    const int R = fstream_bucket(t.radius);
+    if (g.inner == 1) {
+        p.gpr = (g.n_out + FROW_P - 1) / FROW_P;
+        const uintptr_t a = reinterpret_cast<uintptr_t>(g.in) | reinterpret_cast<uintptr_t>(g.out);
+        p.row_aligned = ((a & 15) == 0 && g.n_in % 4 == 0 && g.n_out % 4 == 0) ? 1 : 0;
+    } else {
+        p.xblocks = (int32_t)((g.inner / fcols(R) + 127) / 128);
+    }
+    switch (R) {
+    case 1: return launch_fstream<1>(p, t, s);
+    case 2: return launch_fstream<2>(p, t, s);
+    case 3: return launch_fstream<3>(p, t, s);
+    case 4: return launch_fstream<4>(p, t, s);
+    case 6: return launch_fstream<6>(p, t, s);
+    case 8: return launch_fstream<8>(p, t, s);
+    case 12: return launch_fstream<12>(p, t, s);
+    case 16: return launch_fstream<16>(p, t, s);
+    default: return cudaErrorInvalidValue;
+    }
+}
+
+}  // namespace sepfilt

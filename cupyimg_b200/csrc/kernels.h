@@ -63,6 +63,9 @@ struct F32Line {
     float        cval;
 };
 bool        f32_line_supported(const F32Line& g, int radius);
+// register-streaming versions (f32_stream.cu) for vector-aligned geometries; same contract
+bool        f32_stream_supported(const F32Line& g, int radius);
+cudaError_t launch_f32_stream(const F32Line& g, const F32Taps& t, cudaStream_t s);
 cudaError_t launch_f32_corr1d(const F32Line& g, const F32Taps& t, cudaStream_t s);
 
 // ---- fused multi-axis f32 (fused3d.cu) ----
