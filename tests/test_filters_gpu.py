@@ -445,3 +445,37 @@ def test_f32_radius_9_to_16(mode, ndi):
             expect = len(shape) - (1 if launches == 1 else 0) if mode == "wrap" else launches
             assert _ffi.LAUNCHES == expect, (shape, sigma, _ffi.LAUNCHES)
             assert_f32_close(got, want, atol_scale=2e-6)
+
+
+@pytest.mark.parametrize("mode", ["reflect", "constant", "nearest", "mirror", "wrap"])
+def test_f32_streaming_single_axis_passes(mode, ndi):
+    """csrc/f32_stream.cu: column pass (radius <= 8) and row pass (radius <= 4) without shared memory, on
+    aligned shapes with several segments / long rows, origins, short lines, and the windowed call."""
+    from cupyimg_b200 import _array
+    from cupyimg_b200.scipy.ndimage import filters as F
+    import torch
+    rng = np.random.default_rng(44)
+    for shape, axes in [((3, 700, 64), (0, 1, 2)), ((2, 37, 2056), (1, 2)), ((5, 6, 8), (0, 1, 2)), ((40, 12), (0, 1))]:
+        x = rng.random(shape).astype(np.float32)
+        xd = to_device(x)
+        for axis in axes:
+            for radius, order in [(1, 0), (2, 0), (3, 1), (4, 0), (6, 0), (8, 0), (8, 1)]:
+                w = oracle.gaussian_kernel1d(max(radius / 3.0, 0.6), order, radius)[::-1].copy()
+                for origin in (0, -radius, radius // 2):
+                    want = oracle.correlate1d(x, w, axis=axis, mode=mode, cval=0.75, origin=origin)
+                    got = to_host(ndi.correlate1d(xd, w, axis=axis, mode=mode, cval=0.75, origin=origin))
+                    if order:
+                        # derivative taps cancel: the float32 rounding error scales with the INPUT, not with
+                        # the (near-zero) output — the reference's own absolute setting (SURVEY 8d)
+                        assert_f32_close(got, want, atol=1e-6)
+                    else:
+                        assert_f32_close(got, want, atol_scale=2e-6)
+    x = rng.random((64, 24, 64)).astype(np.float32)
+    xd = to_device(x)
+    w = oracle.gaussian_kernel1d(2.0, 0, 8)[::-1].copy()
+    full = to_host(ndi.correlate1d(xd, w, axis=0, mode=mode, cval=0.75))
+    spec = F._PassSpec(0, w, 0, F._check_mode(mode))
+    for off, n in ((0, 64), (9, 30), (40, 24), (63, 1)):
+        out = torch.empty((n, 24, 64), dtype=torch.float32, device="cuda")
+        F._launch_pass(_array.ingest(xd), _array.ingest(out), spec, 0.75, False, in_offset=off)
+        np.testing.assert_array_equal(to_host(out), full[off:off + n])
