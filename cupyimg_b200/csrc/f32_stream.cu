@@ -156,6 +156,11 @@ f32_stream_row_kernel(const __grid_constant__ FStreamParams p)
     const float* __restrict__ src = p.in + row * p.n_in;
     const int g0 = x + p.shift - 4 * H;                      // source index of win[0]
     const bool vec_ok = p.row_aligned && (p.shift & 3) == 0;
+    // Aligned rows (the common case): the halo of the first / last thread of a row is the mirror image of
+    // elements the thread already holds, so it is filled by register selects instead of an element-wise
+    // gather (which cost a second round of dependent loads in every warp holding an edge thread).
+    const bool reg_edges = vec_ok && p.shift == 0 && p.n_in == p.n_out && (p.n_in & 7) == 0 && p.n_in >= 16 &&
+                           p.mode != SEPFILT_WRAP && H <= 2;
     float win[4 * NW];
 #pragma unroll
     for (int j = 0; j < NW; ++j) {
@@ -163,11 +168,30 @@ f32_stream_row_kernel(const __grid_constant__ FStreamParams p)
         if (vec_ok && g >= 0 && g + 4 <= p.n_in) {
             const float4 v = *reinterpret_cast<const float4*>(src + g);
             win[4 * j] = v.x; win[4 * j + 1] = v.y; win[4 * j + 2] = v.z; win[4 * j + 3] = v.w;
+        } else if (reg_edges) {
+            win[4 * j] = win[4 * j + 1] = win[4 * j + 2] = win[4 * j + 3] = p.cval;   // constant mode; others below
         } else {
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 const int m = fremap_fast(p.mode, g + e, p.n_in);
                 win[4 * j + e] = m < 0 ? p.cval : src[m];
+            }
+        }
+    }
+    if (reg_edges && p.mode != SEPFILT_CONSTANT) {
+        const int e = p.mode == SEPFILT_REFLECT ? 1 : 0;     // reflect: d c b a | a b c d ; mirror: d c b | a b c d
+        if (x == 0) {                                        // win[i], i < 4H, is array column i - 4H
+#pragma unroll
+            for (int i = 0; i < 4 * H; ++i) {
+                const float refl = win[8 * H - 1 - i], mirr = win[8 * H - i];
+                win[i] = p.mode == SEPFILT_NEAREST ? win[4 * H] : (e ? refl : mirr);
+            }
+        }
+        if (x + FROW_P == p.n_in) {                          // win[i], i >= 4H + 8, is array column n + (i - 4H - 8)
+#pragma unroll
+            for (int i = 4 * H + 8; i < 8 * H + 8; ++i) {
+                const float refl = win[8 * H + 15 - i], mirr = win[8 * H + 14 - i];
+                win[i] = p.mode == SEPFILT_NEAREST ? win[4 * H + 7] : (e ? refl : mirr);
             }
         }
     }
@@ -244,11 +268,11 @@ bool f32_stream_supported(const F32Line& g, int radius)
 {
     const int R = fstream_bucket(radius);
     if (R < 0) return false;
-    // Measured on 512^3 (tools/time_f32_1d.py, ms, streaming vs shared-memory tile): 5 taps 0.16-0.17 vs
-    // 0.23-0.25 (95-101 % of the measured copy bandwidth), 9 taps 0.19-0.20 vs 0.24-0.25, 17 taps column
-    // 0.252 vs 0.27 but row 0.352 vs 0.296 (every warp of a 512-wide row holds an edge thread whose
-    // element-wise halo gather grows with the radius), 25 / 33 taps 0.34-0.67 vs 0.30-0.35.
-    if (g.inner == 1 ? R > 4 : R > 8) return false;
+    // Measured on 512^3 (tools/time_f32_1d.py, ms, streaming vs shared-memory tile): row pass 5 / 9 / 17 taps
+    // 0.156 / 0.160 / 0.189 vs 0.245 / 0.253 / 0.296 (87-105 % of the measured copy bandwidth; with an
+    // element-wise halo gather in the edge threads the 17-tap row pass took 0.352), column pass 0.170 / 0.19 /
+    // 0.252 vs 0.23 / 0.24 / 0.27; 25 / 33 taps 0.34-0.67 vs 0.30-0.35: radius 12 / 16 stay on the tiles.
+    if (R > 8) return false;
     if (g.n_in <= 0 || g.n_out <= 0 || g.outer <= 0 || g.inner <= 0) return false;
     const uintptr_t a = reinterpret_cast<uintptr_t>(g.in) | reinterpret_cast<uintptr_t>(g.out);
     if (g.inner == 1) {
