@@ -249,6 +249,12 @@ exact_stream_row_kernel(const __grid_constant__ StreamParams p)
     const T* __restrict__ src = reinterpret_cast<const T*>(p.in) + row * p.n_in;
     const int g0 = x + p.shift - H * E;                      // source index of win[0]
     const bool vec_ok = p.row_aligned && (p.shift % E) == 0;
+    // Aligned rows: the halo of the first / last thread of a row mirrors elements the thread already holds,
+    // so it is filled by register selects after the conversion instead of an element-wise gather (a second
+    // round of dependent loads in every warp that holds an edge thread).
+    constexpr int HE = H * E;
+    const bool reg_edges = vec_ok && p.shift == 0 && p.n_in == p.n_out && (p.n_in % ROW_P) == 0 &&
+                           p.n_in >= 2 * ROW_P && p.mode != SEPFILT_WRAP && HE <= ROW_P;
 
     double win[(NCH + 2 * H) * E];
 #pragma unroll
@@ -258,11 +264,31 @@ exact_stream_row_kernel(const __grid_constant__ StreamParams p)
             const P v = *reinterpret_cast<const P*>(src + g);
 #pragma unroll
             for (int e = 0; e < E; ++e) win[j * E + e] = (double)v.v[e];
+        } else if (reg_edges) {
+#pragma unroll
+            for (int e = 0; e < E; ++e) win[j * E + e] = p.cval;      // constant mode; the others below
         } else {
 #pragma unroll
             for (int e = 0; e < E; ++e) {
                 const int m = remap_fast(p.mode, g + e, p.n_in);
                 win[j * E + e] = m < 0 ? p.cval : (double)src[m];
+            }
+        }
+    }
+    if (reg_edges && p.mode != SEPFILT_CONSTANT) {
+        const bool refl = p.mode == SEPFILT_REFLECT, near = p.mode == SEPFILT_NEAREST;
+        if (x == 0) {                                        // win[i], i < HE, is array column i - HE
+#pragma unroll
+            for (int i = 0; i < HE; ++i) {
+                const double a = win[2 * HE - 1 - i], b = win[2 * HE - i];
+                win[i] = near ? win[HE] : (refl ? a : b);
+            }
+        }
+        if (x + ROW_P == p.n_in) {                           // win[i], i >= HE + ROW_P, is array column n + (i - HE - ROW_P)
+#pragma unroll
+            for (int i = HE + ROW_P; i < 2 * HE + ROW_P; ++i) {
+                const double a = win[2 * (HE + ROW_P) - 1 - i], b = win[2 * (HE + ROW_P) - 2 - i];
+                win[i] = near ? win[HE + ROW_P - 1] : (refl ? a : b);
             }
         }
     }

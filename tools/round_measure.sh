@@ -9,6 +9,8 @@ python bench.py --steps 20 --warmup 3 > $O/${R}_bench_n1.json 2> $O/${R}_bench_n
 python tools/time_configs.py > $O/${R}_config_timings.txt 2>/dev/null
 python tools/time_c3.py >> $O/${R}_config_timings.txt 2>/dev/null
 python tools/time_gradmag.py >> $O/${R}_config_timings.txt 2>/dev/null
+python tools/time_f32_1d.py >> $O/${R}_config_timings.txt 2>/dev/null
+python tools/time_e2e.py 32 >> $O/${R}_config_timings.txt 2>/dev/null
 python tools/time_fused.py 512 2.0 reflect constant nearest mirror wrap >> $O/${R}_config_timings.txt 2>/dev/null
 # launch list of the bench command (cold-cache, serialised: shares, not absolutes)
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/${R}_ncu_launch_list_bench.csv \
