@@ -62,6 +62,10 @@ __host__ __device__ constexpr int rup4(int r) { return (r + 3) & ~3; }
 // TX: tile width along the contiguous axis; NT = TX * TYM / 4 threads (one float4 column group x one
 // row each in the x+z pass); G: planes per pipeline group; CTAS: co-resident CTAs per SM.
 // RY: rows per y-pass register tile; a tile of ty <= 2 * RY rows is covered by two row halves.
+// (Three 5-row parts, i.e. 432 y-pass items spread over 13.5 warps so that every warp carries both x+z and
+//  y work — the CTA barrier is 17.5 % of the warp time because the 7 warps without y items idle — were
+//  measured: 0.297 -> 0.310 ms constant, 0.329 -> 0.373 ms reflect on 512^3: 37 % more shared-memory loads
+//  and no idle warp left for the edge patch cost more than the balance gains.)
 template <int R, int TX_, int G_, int CTAS_, int RY_ = 8> struct Cfg {
     static constexpr int TX = TX_, NT = TX_ * TYM / 4, CTAS = CTAS_, RY = RY_;
     static constexpr int HL = rup4(R);                 // x halo staged (multiple of 4 floats)
