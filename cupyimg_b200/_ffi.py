@@ -58,7 +58,7 @@ class Pass(ctypes.Structure):
 
 EXPORTS = (
     "sepfilt_version", "sepfilt_last_error", "sepfilt_correlate1d", "sepfilt_separable_f32",
-    "sepfilt_separable_f32_supported", "sepfilt_gradmag_step", "sepfilt_copy_cast",
+    "sepfilt_separable_f32_supported", "sepfilt_gradmag_step", "sepfilt_copy_cast", "sepfilt_correlate_nd",
 )
 
 _lib = None
@@ -97,6 +97,9 @@ def lib():
         L.sepfilt_separable_f32_supported.restype = ci
         L.sepfilt_gradmag_step.argtypes = [vp, vp, i64, ci, ci, vp]
         L.sepfilt_gradmag_step.restype = ci
+        i32p = ctypes.POINTER(ctypes.c_int32)
+        L.sepfilt_correlate_nd.argtypes = [TP, TP, ctypes.POINTER(dbl), i32p, i32p, ci, dbl, vp, ctypes.c_size_t, vp]
+        L.sepfilt_correlate_nd.restype = ci
         L.sepfilt_copy_cast.argtypes = [TP, TP, vp]
         L.sepfilt_copy_cast.restype = ci
         _lib = L

@@ -371,6 +371,63 @@ int sepfilt_gradmag_step(void* acc, const void* a, int64_t n, int dtype, int op,
     return SEPFILT_OK;
 }
 
+int sepfilt_correlate_nd(const sepfilt_tensor* in, const sepfilt_tensor* out,
+                         const double* weights, const int32_t* wshape, const int32_t* origin,
+                         int mode, double cval, void* scratch, size_t scratch_bytes, void* stream)
+{
+    int rc;
+    if ((rc = check_tensor(in, "input", false)) || (rc = check_tensor(out, "output", true))) return rc;
+    if (in->ndim != out->ndim) return fail(SEPFILT_ERR_INVALID, "input and output rank differ");
+    if (in->ndim < 1) return fail(SEPFILT_ERR_INVALID, "rank must be >= 1");
+    if (!weights || !wshape || !origin) return fail(SEPFILT_ERR_INVALID, "no filter weights given");
+    if (mode < SEPFILT_REFLECT || mode > SEPFILT_WRAP) return fail(SEPFILT_ERR_INVALID, "boundary mode not supported");
+    if (in->device != out->device) return fail(SEPFILT_ERR_INVALID, "input and output on different devices");
+    CorrNdParams p;
+    std::memset(&p, 0, sizeof p);
+    int64_t K = 1;
+    for (int d = 0; d < in->ndim; ++d) {
+        if (in->shape[d] != out->shape[d]) return fail(SEPFILT_ERR_INVALID, "output shape not correct");
+        if (wshape[d] < 1) return fail(SEPFILT_ERR_INVALID, "filter weights array has incorrect shape");
+        const int before = wshape[d] / 2 + origin[d];
+        if (before < 0 || before >= wshape[d]) return fail(SEPFILT_ERR_INVALID, "invalid origin");
+        K *= wshape[d];
+        if (K > SEPFILT_MAX_TAPS) return fail(SEPFILT_ERR_INVALID, "more than %d filter weights", SEPFILT_MAX_TAPS);
+        p.shape[d] = in->shape[d];
+        p.istride[d] = in->stride_bytes[d];
+        p.ostride[d] = out->stride_bytes[d];
+        p.wshape[d] = wshape[d];
+        p.before[d] = before;
+    }
+    p.total = numel(out);
+    if (p.total == 0) return SEPFILT_OK;
+    if (!in->ptr || !out->ptr) return fail(SEPFILT_ERR_INVALID, "NULL data pointer");
+    DeviceGuard guard(in->device);
+    if (guard.err != cudaSuccess) return fail_cuda(guard.err, "cudaSetDevice");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    p.in = static_cast<const char*>(in->ptr);
+    p.out = static_cast<char*>(out->ptr);
+    p.in_dtype = in->dtype;
+    p.out_dtype = out->dtype;
+    p.ndim = in->ndim;
+    p.K = (int32_t)K;
+    p.mode = mode;
+    p.cval = cval;
+    if (K <= SEPFILT_PARAM_TAPS) {
+        std::memcpy(p.w, weights, sizeof(double) * (size_t)K);
+    } else {
+        const size_t need = sizeof(double) * (size_t)K;
+        if (!scratch || scratch_bytes < need)
+            return fail(SEPFILT_ERR_SCRATCH, "more than %d filter weights need %zu bytes of device scratch",
+                        SEPFILT_PARAM_TAPS, need);
+        cudaError_t e = cudaMemcpyAsync(scratch, weights, need, cudaMemcpyHostToDevice, s);
+        if (e != cudaSuccess) return fail_cuda(e, "cudaMemcpyAsync(weights)");
+        p.wdev = static_cast<const double*>(scratch);
+    }
+    cudaError_t e = launch_correlate_nd(p, s);
+    if (e != cudaSuccess) return fail_cuda(e, "correlate_nd launch");
+    return SEPFILT_OK;
+}
+
 int sepfilt_copy_cast(const sepfilt_tensor* in, const sepfilt_tensor* out, void* stream)
 {
     // a 1-tap identity correlation is a strided copy under the store's cast rules

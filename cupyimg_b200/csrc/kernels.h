@@ -29,6 +29,25 @@ struct ExactParams {
 cudaError_t launch_exact_corr1d(const ExactParams& p, cudaStream_t s);
 cudaError_t launch_gradmag_step(void* acc, const void* a, int64_t n, int dtype, int op, cudaStream_t s);
 
+// ---- dense N-d correlation, exact arithmetic (correlate_nd.cu) ----
+struct CorrNdParams {
+    const char* in;
+    char*       out;
+    int32_t     in_dtype, out_dtype;
+    int32_t     ndim, K;                    // K = product of wshape
+    int64_t     shape[SEPFILT_MAX_NDIM];    // input == output extents
+    int64_t     istride[SEPFILT_MAX_NDIM];
+    int64_t     ostride[SEPFILT_MAX_NDIM];
+    int32_t     wshape[SEPFILT_MAX_NDIM];
+    int32_t     before[SEPFILT_MAX_NDIM];   // wshape / 2 + origin per axis
+    int64_t     total;
+    int32_t     mode;
+    double      cval;
+    const double* wdev;                     // weights in device memory (K > SEPFILT_PARAM_TAPS) or nullptr
+    double      w[SEPFILT_PARAM_TAPS];
+};
+cudaError_t launch_correlate_nd(const CorrNdParams& p, cudaStream_t s);
+
 // ---- exact path, tiled (exact_tiled.cu): C-contiguous arrays, odd symmetric / anti-symmetric taps ----
 struct ExactTiledGeom {
     const void* in;

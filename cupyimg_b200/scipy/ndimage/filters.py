@@ -10,6 +10,7 @@ Drop-in for the functions on the reference's separable hot path
     generic_laplace :963    laplace :1041    gaussian_laplace :1077
     generic_gradient_magnitude :1125    gaussian_gradient_magnitude :1207
     minimum_filter / maximum_filter :1296-1396 (separable sizes)    minimum_filter1d / maximum_filter1d :1422-1508
+    correlate :65    convolve :136 (dense N-d weights, exact arithmetic)
 
 Inputs are CUDA arrays (``torch.Tensor``, ``cupy.ndarray`` or anything exposing
 ``__cuda_array_interface__`` / ``__dlpack__``); the result is the same kind of object.
@@ -42,6 +43,7 @@ __all__ = [
     "generic_laplace", "laplace", "gaussian_laplace",
     "generic_gradient_magnitude", "gaussian_gradient_magnitude",
     "minimum_filter1d", "maximum_filter1d", "minimum_filter", "maximum_filter",
+    "correlate", "convolve",
 ]
 
 _F32 = np.dtype("float32")
@@ -807,3 +809,67 @@ def maximum_filter(input, size=None, footprint=None, output=None, mode="reflect"
                    axes=None):
     """Multi-dimensional maximum filter (reference filters.py:1335-1370), separable case."""
     return _min_or_max_filter(input, size, footprint, output, mode, cval, origin, _MAX, axes)
+
+
+# ----------------------------------------------------------------------------
+# dense N-d correlation for small kernels (SURVEY §8(f) rank 3)
+# ----------------------------------------------------------------------------
+def _correlate_or_convolve(input, weights, output, mode, cval, origin, convolution):
+    """reference filters.py:441-495 for N-d weights: validation (_filters_core._check_nd_args, :63-76),
+    the convolution flip / origin rule (:459-466), one launch (sepfilt_correlate_nd) in scipy's arithmetic."""
+    import ctypes
+    inp = _ingest_input(input)
+    w = _host_taps(weights)
+    if inp.dtype.kind == "c" or w.dtype.kind == "c":
+        raise NotImplementedError("complex-valued N-d correlation is not on this path (1-D weights are: correlate1d)")
+    wshape = [s for s in w.shape if s != 0]
+    if w.ndim != inp.ndim or len(wshape) != inp.ndim:
+        raise RuntimeError("filter weights array has incorrect shape.")
+    if not isinstance(mode, str) and hasattr(mode, "__iter__"):
+        raise RuntimeError("A sequence of modes is not supported")
+    mode_code = _check_mode(mode)
+    origins = [int(o) for o in _normalize_sequence(origin, inp.ndim)]
+    if convolution:
+        w = w[tuple([slice(None, None, -1)] * w.ndim)]
+        for i in range(len(origins)):
+            origins[i] = -origins[i]
+            if not w.shape[i] & 1:
+                origins[i] -= 1
+    for o, width in zip(origins, wshape):
+        _check_origin(o, width)
+    cval, _ = _split_cval(cval, False)
+    out, _ = _get_output(output, inp)
+    if out.size == 0:
+        return _array.export(out, inp)
+    w = np.ascontiguousarray(w, dtype=np.float64)
+    dst = out
+    if inp.may_overlap(out):
+        dst = _array.empty(out.shape, out.dtype, out.device)     # _filters_core.py:148-155
+    scratch, sptr, sbytes = None, None, 0
+    if w.size > _ffi.PARAM_TAPS:
+        if w.size > _ffi.MAX_TAPS:
+            raise NotImplementedError("more than %d filter weights: use an FFT-based convolution" % _ffi.MAX_TAPS)
+        scratch = _array.empty((w.size,), np.float64, inp.device)
+        sptr, sbytes = scratch.ptr, w.size * 8
+    i32 = ctypes.c_int32 * inp.ndim
+    rc = _ffi.lib().sepfilt_correlate_nd(inp.tensor(), dst.tensor(), w.ctypes.data_as(ctypes.POINTER(ctypes.c_double)),
+                                         i32(*wshape), i32(*origins), mode_code, float(cval), sptr, sbytes,
+                                         _array.current_stream(inp.device))
+    _ffi.check(rc)
+    _ffi.count_launch()
+    if dst is not out:
+        _copy_cast(dst, out)
+    del scratch
+    return _array.export(out, inp)
+
+
+def correlate(input, weights, output=None, mode="reflect", cval=0.0, origin=0, *, dtype_mode=None):
+    """Multi-dimensional correlation with a small dense kernel (reference filters.py:65-133)."""
+    _check_dtype_mode(dtype_mode)
+    return _correlate_or_convolve(input, weights, output, mode, cval, origin, False)
+
+
+def convolve(input, weights, output=None, mode="reflect", cval=0.0, origin=0, *, dtype_mode=None):
+    """Multi-dimensional convolution with a small dense kernel (reference filters.py:136-210)."""
+    _check_dtype_mode(dtype_mode)
+    return _correlate_or_convolve(input, weights, output, mode, cval, origin, True)

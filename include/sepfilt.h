@@ -164,6 +164,20 @@ SEPFILT_API int sepfilt_separable_f32_supported(const sepfilt_tensor* in, const 
  * a and acc are C-contiguous arrays of `dtype` with n elements. */
 SEPFILT_API int sepfilt_gradmag_step(void* acc, const void* a, int64_t n, int dtype, int op, void* stream);
 
+/*
+ * Dense N-d correlation with a small N-d weights array: replaces one
+ * `kernel(input, weights, output)` launch of _filters_core._call_kernel (_filters_core.py:152) for the
+ * kernel _get_correlate_kernel builds from N-d weights (filters.py:498-511; callers correlate / convolve,
+ * filters.py:65-210).   out[i] = sum_k w[k] * in[remap(i + k - (wshape/2 + origin))]  per axis, in scipy's
+ * arithmetic (float64, taps with |w| > DBL_EPSILON in C order, no FMA contraction, C-cast store).
+ *  - in / out: same shape, any dtype pair, any byte strides, must not overlap;
+ *  - weights: HOST doubles, C order, rank = in->ndim, extents wshape[]; origin[] per axis;
+ *  - scratch: only read when the number of taps exceeds SEPFILT_PARAM_TAPS (needs taps * 8 bytes, device).
+ */
+SEPFILT_API int sepfilt_correlate_nd(const sepfilt_tensor* in, const sepfilt_tensor* out,
+                         const double* weights, const int32_t* wshape, const int32_t* origin,
+                         int mode, double cval, void* scratch, size_t scratch_bytes, void* stream);
+
 /* Strided copy with dtype conversion under the same cast rules as the filter store
  * (used for the "no axes to filter -> output[...] = input[...]" branches, filters.py:663-664). */
 SEPFILT_API int sepfilt_copy_cast(const sepfilt_tensor* in, const sepfilt_tensor* out, void* stream);

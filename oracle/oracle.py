@@ -465,3 +465,63 @@ def minimum_filter(input, size=3, output=None, mode="reflect", cval=0.0, origin=
 
 def maximum_filter(input, size=3, output=None, mode="reflect", cval=0.0, origin=0):
     return _min_or_max_filter(input, size, output, mode, cval, origin, "max")
+
+
+# ---- dense N-d correlation -------------------------------------------
+def _correlate_nd(input, weights, output, mode, cval, origin, convolution):
+    """The reference's generated N-d correlate kernel (filters.py:441-495, body _filters_core.py:239-312)
+    in scipy's NI_Correlate arithmetic: float64 `tmp += x * w` over the taps with |w| > DBL_EPSILON in C order
+    of the weights, boundary extension per axis (_util.py:170-228), C-cast store."""
+    input = np.asarray(input)
+    w = np.asarray(weights, np.float64)
+    if w.ndim != input.ndim or any(s == 0 for s in w.shape):
+        raise RuntimeError("filter weights array has incorrect shape.")
+    if mode not in MODES:
+        raise RuntimeError("boundary mode not supported")
+    origins = [int(o) for o in _seq(origin, input.ndim)]
+    if convolution:
+        w = w[tuple([slice(None, None, -1)] * w.ndim)]
+        for i in range(len(origins)):
+            origins[i] = -origins[i]
+            if not w.shape[i] & 1:
+                origins[i] -= 1
+    for o, width in zip(origins, w.shape):
+        if width // 2 + o < 0 or width // 2 + o >= width:
+            raise ValueError("invalid origin")
+    output = _get_output(output, input)
+    if input.size == 0:
+        return output
+    x = input.astype(np.float64)
+    acc = np.zeros(input.shape, np.float64)
+    # per axis and tap offset: index vector through the boundary rule (-1 -> cval)
+    maps = []
+    for d, n in enumerate(input.shape):
+        before = w.shape[d] // 2 + origins[d]
+        maps.append([np.array([remap(mode, i + k - before, n) for i in range(n)], np.int64) for k in range(w.shape[d])])
+    for kk in np.ndindex(*w.shape):
+        wk = w[kk]
+        if not abs(wk) > np.finfo(np.float64).eps:
+            continue
+        v = x
+        outside = np.zeros(input.shape, bool)
+        for d, k in enumerate(kk):
+            m = maps[d][k]
+            v = np.take(v, np.where(m < 0, 0, m), axis=d)
+            shape = [1] * input.ndim
+            shape[d] = -1
+            outside |= (m < 0).reshape(shape)
+        v = np.where(outside, float(cval), v)
+        acc = acc + v * wk
+    res = np.empty(input.shape, output.dtype)
+    acc = np.ascontiguousarray(acc)
+    lib().oracle_copy_cast(acc.ctypes.data, _DT[np.dtype(np.float64)], res.ctypes.data, _DT[res.dtype], acc.size)
+    output[...] = res
+    return output
+
+
+def correlate(input, weights, output=None, mode="reflect", cval=0.0, origin=0):
+    return _correlate_nd(input, weights, output, mode, cval, origin, False)
+
+
+def convolve(input, weights, output=None, mode="reflect", cval=0.0, origin=0):
+    return _correlate_nd(input, weights, output, mode, cval, origin, True)

@@ -194,3 +194,62 @@ def test_minmax_oracle_known_answers_and_scipy():
             got = getattr(oracle, fn + "_filter")(x, size=[size, 1, 3], mode=mode, cval=-2.0, output=np.float32)
             want = getattr(sndi, fn + "_filter")(x, size=[size, 1, 3], mode=mode, cval=-2.0, output=np.float32)
             np.testing.assert_array_equal(got, want)
+
+
+# the reference's literal known answers for dense N-d correlate / convolve (tests/test_ndimage.py:214-341):
+# (input, kernel, kwargs, expected correlate, expected convolve); "all" sweeps the 10 x 10 dtype matrix
+A23 = [[1, 2, 3], [4, 5, 6]]
+CORRELATE_ND_KATS = [
+    (A23, [[1, 1], [1, 1]], {}, [[4, 6, 10], [10, 12, 16]], [[12, 16, 18], [18, 22, 24]], None),          # correlate11
+    (A23, [[1, 0], [0, 1]], {}, [[2, 3, 5], [5, 6, 8]], [[6, 8, 9], [9, 11, 12]], "all"),                  # correlate12-14
+    (A23, [[0.5, 0], [0, 0.5]], {"output": "float32"}, [[1, 1.5, 2.5], [2.5, 3, 4]], [[3, 4, 4.5], [4.5, 5.5, 6]], "in"),   # correlate16
+    ([1, 2, 3], [1, 1], {"origin": -1}, [3, 5, 6], [2, 3, 5], None),                                        # correlate17
+    (A23, [[1, 0], [0, 1]], {"output": "float32", "mode": "nearest", "origin": -1},
+     [[6, 8, 9], [9, 11, 12]], [[2, 3, 5], [5, 6, 8]], "in"),                                               # correlate18
+    (A23, [[1, 0], [0, 1]], {"output": "float32", "mode": "nearest", "origin": [-1, 0]},
+     [[5, 6, 8], [8, 9, 11]], [[3, 5, 6], [6, 8, 9]], "in"),                                                # correlate19
+]
+
+
+def run_correlate_nd_kats(ns, to_dev=lambda a: a, to_np=lambda a: a):
+    for x, k, kw, want_cor, want_cov, sweep in CORRELATE_ND_KATS:
+        in_types = TYPES if sweep in ("all", "in") else ["int64"]
+        out_types = TYPES if sweep == "all" else [None]
+        for t1 in in_types:
+            for t2 in out_types:
+                kw2 = dict(kw)
+                if t2 is not None:
+                    kw2["output"] = np.dtype(t2)
+                elif "output" in kw2:
+                    kw2["output"] = np.dtype(kw2["output"])
+                for fn, want in (("correlate", want_cor), ("convolve", want_cov)):
+                    got = to_np(getattr(ns, fn)(to_dev(np.asarray(x, dtype=t1)), np.asarray(k, float), **kw2))
+                    np.testing.assert_array_equal(got.astype(np.float64), np.asarray(want, float), err_msg=fn)
+                    if "output" in kw2:
+                        assert got.dtype == kw2["output"]
+
+
+def test_correlate_nd_oracle_known_answers_and_scipy():
+    """the oracle's N-d correlate against the reference's known answers and scipy,
+    bit for bit (integer dtypes included: scipy's tap order and cast)."""
+    run_correlate_nd_kats(oracle)
+    e = oracle.correlate(np.zeros((1, 0)), np.ones((1, 2)))          # correlate10: empty in, empty out
+    assert e.shape == (1, 0)
+    rng = np.random.default_rng(0)
+    for dt in ["uint8", "int16", "int64", "float32", "float64"]:
+        for shape, wshapes in [((9, 11), [(3, 3), (2, 4), (5, 1)]), ((5, 6, 7), [(3, 3, 3), (2, 1, 4)]), ((12,), [(5,), (4,)])]:
+            x = (rng.random(shape) * 100 - (0 if dt[0] == "u" else 30)).astype(dt)
+            for ws in wshapes:
+                w = rng.standard_normal(ws)
+                w[tuple(0 for _ in ws)] = 0.0
+                for mode in ["reflect", "constant", "nearest", "mirror", "wrap"]:
+                    for origin in (0, [-(s // 2) for s in ws], [(s - 1) // 2 for s in ws]):
+                        for fn in ("correlate", "convolve"):
+                            got = getattr(oracle, fn)(x, w, mode=mode, cval=2.5, origin=origin)
+                            want = getattr(sndi, fn)(x, w, mode=mode, cval=2.5, origin=origin)
+                            assert got.dtype == want.dtype
+                            np.testing.assert_array_equal(got, want)
+    with pytest.raises(RuntimeError):
+        oracle.correlate(np.ones((3, 3)), np.ones(3))
+    with pytest.raises(ValueError):
+        oracle.correlate(np.ones((3, 3)), np.ones((3, 3)), origin=2)

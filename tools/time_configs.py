@@ -36,3 +36,14 @@ oi = torch.empty_like(img)
 w = np.exp(-0.5 * (np.arange(-4, 5) / 1.5) ** 2); w /= w.sum()
 timeit("C3 convolve1d 9 taps axis=1 8x2048^2 u16 mirror (exact)", lambda: ndi.convolve1d(img, w, axis=1, output=oi, mode="mirror"), 8 * 2048 * 2048, 4, reps=5)
 timeit("C3 convolve1d 9 taps axis=2 8x2048^2 u16 mirror (exact)", lambda: ndi.convolve1d(img, w, axis=2, output=oi, mode="mirror"), 8 * 2048 * 2048, 4, reps=5)
+
+# SURVEY 8(f) ranks 2 and 3 (general per-element exact kernels)
+x = torch.rand((512, 512, 512), device="cuda"); o = torch.empty_like(x)
+timeit("   maximum_filter size=5 512^3 f32 (3 exact window passes)", lambda: ndi.maximum_filter(x, 5, output=o), 512**3, 8, reps=5)
+timeit("   maximum_filter1d size=5 axis=2 512^3 f32", lambda: ndi.maximum_filter1d(x, 5, axis=2, output=o), 512**3, 8, reps=5)
+del x, o
+im = torch.rand((8, 2048, 2048), device="cuda"); oi2 = torch.empty_like(im)
+k33 = np.arange(9.0).reshape(1, 3, 3) / 36
+timeit("   correlate 1x3x3 on 8x2048^2 f32 (exact N-d kernel)", lambda: ndi.correlate(im, k33, output=oi2), 8 * 2048 * 2048, 8, reps=5)
+k55 = np.arange(25.0).reshape(1, 5, 5) / 300
+timeit("   correlate 1x5x5 on 8x2048^2 f32 (exact N-d kernel)", lambda: ndi.correlate(im, k55, output=oi2), 8 * 2048 * 2048, 8, reps=5)
