@@ -187,6 +187,31 @@ int sepfilt_correlate1d(const sepfilt_tensor* in, const sepfilt_tensor* out,
     }
 
     // ---- exact path, tiled kernels where the geometry and the taps allow ----
+    if ((pass->uniform == 0 || pass->uniform > 1) && c_contiguous(in) && c_contiguous(out)) {
+        ExactTiledGeom g;
+        g.in = in->ptr;
+        g.out = out->ptr;
+        g.in_dtype = in->dtype;
+        g.out_dtype = out->dtype;
+        g.outer = 1;
+        g.inner = 1;
+        for (int d = 0; d < axis; ++d) g.outer *= in->shape[d];
+        for (int d = axis + 1; d < in->ndim; ++d) g.inner *= in->shape[d];
+        g.n_in = in->shape[axis];
+        g.n_out = out->shape[axis];
+        g.shift = in_offset - pass->origin;
+        if (pass->uniform > 1) {
+            // minimum / maximum window: streaming kernels for the dtype-preserving common cases
+            g.shift = in_offset;
+            static const bool no_mm = getenv("SEPFILT_NO_MINMAX_STREAM") != nullptr;   // A/B aid
+            if (!no_mm && pass->uniform <= 3 && minmax_stream_supported(g, pass->ntaps, pass->origin, cval)) {
+                cudaError_t e = launch_minmax_stream(g, pass->ntaps, pass->origin, pass->mode, cval,
+                                                     pass->uniform == 3, s);
+                if (e != cudaSuccess) return fail_cuda(e, "minmax_stream launch");
+                return SEPFILT_OK;
+            }
+        }
+    }
     if (!pass->uniform && c_contiguous(in) && c_contiguous(out)) {
         const int sym = probe_symmetry(pass->taps, pass->ntaps);
         ExactTiledGeom g;

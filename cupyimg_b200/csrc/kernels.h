@@ -66,6 +66,11 @@ bool        exact_stream_supported(const ExactTiledGeom& g, int K, int symmetric
 cudaError_t launch_exact_stream(const ExactTiledGeom& g, const double* taps, int K, int symmetric, int mode,
                                 double cval, cudaStream_t s);
 
+// ---- minimum / maximum window passes, register streaming (minmax_stream.cu) ----
+bool        minmax_stream_supported(const ExactTiledGeom& g, int S, int origin, double cval);
+cudaError_t launch_minmax_stream(const ExactTiledGeom& g, int S, int origin, int mode, double cval, bool is_max,
+                                 cudaStream_t s);
+
 // ---- f32 tiled 1-D passes (f32_1d.cu): C-contiguous (outer, n, inner) view ----
 struct F32Taps {
     int32_t radius;                       // R: taps cover offsets -R..R (zero padded)

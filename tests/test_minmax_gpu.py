@@ -85,3 +85,26 @@ def test_minmax_nd_outputs_views_inplace(ndi):
     m1 = ndi.maximum_filter(big, 5)
     assert bool((m1 >= big).all()) and bool((ndi.minimum_filter(big, 5) <= big).all())
     assert bool((ndi.maximum_filter(m1, 5) >= m1).all())
+
+
+@pytest.mark.parametrize("dtype", ["uint8", "int16", "uint16", "float32", "float64"])
+def test_minmax_streaming_kernels_bit_exact(dtype, ndi):
+    """csrc/minmax_stream.cu (window sizes 2..9, dtype-preserving, vector-aligned shapes): column kernel
+    with several segments, row kernel with long rows, origins, every mode, cvals that fold to T exactly and
+    cvals that do not (fractional, negative for unsigned types, out of range: the general kernel takes over)."""
+    rng = np.random.default_rng(17)
+    for shape, axes in [((3, 150, 64), (0, 1, 2)), ((2, 9, 2064), (1, 2)), ((40, 48), (0, 1))]:
+        if np.dtype(dtype).kind == "f":
+            x = (rng.standard_normal(shape) * 50).astype(dtype)
+        else:
+            info = np.iinfo(dtype)
+            x = rng.integers(info.min, info.max, shape, endpoint=True).astype(dtype)
+        xd = to_device(x)
+        for axis, size, fn in itertools.product(axes, [2, 3, 4, 5, 7, 9], ["minimum_filter1d", "maximum_filter1d"]):
+            for mode, cval in [("reflect", 0.0), ("constant", 3.7), ("constant", -2.5), ("constant", 70000.0),
+                               ("nearest", 0.0), ("mirror", 0.0), ("wrap", 0.0)]:
+                for origin in sorted({0, -(size // 2), (size - 1) // 2}):
+                    want = getattr(oracle, fn)(x, size, axis=axis, mode=mode, cval=cval, origin=origin)
+                    got = to_host(getattr(ndi, fn)(xd, size, axis=axis, mode=mode, cval=cval, origin=origin))
+                    np.testing.assert_array_equal(got, want, err_msg="%s size %d axis %d %s cval %g origin %d" % (
+                        fn, size, axis, mode, cval, origin))
