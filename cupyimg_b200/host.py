@@ -44,6 +44,16 @@ def _run_chunked(x, out, specs, cval, dtype_mode, chunk_planes, device):
     if C < 2 * r:
         C = 2 * r                                            # a chunk must hold its neighbours' halos
     NB = 4
+    chunks = [(z0, min(z0 + C, nz)) for z0 in range(0, nz, C)]
+    # a chunk thinner than the halo cannot serve its neighbours: merge it into its predecessor
+    merged = [chunks[0]]
+    for a, b in chunks[1:]:
+        if b - a < max(r, 1):
+            merged[-1] = (merged[-1][0], b)
+        else:
+            merged.append((a, b))
+    chunks = merged
+    C = max(b - a for a, b in chunks)
     # device chunk buffers laid out [r lower halo | C own planes | r upper halo].  Every plane crosses
     # PCIe exactly once: the halos are filled device-to-device from the neighbouring chunk buffers, so a
     # chunk is filtered one chunk late, when its successor has landed.
@@ -55,13 +65,6 @@ def _run_chunked(x, out, specs, cval, dtype_mode, chunk_planes, device):
     start.record(torch.cuda.current_stream(dev))
     for s in (s_in, s_run, s_out):
         s.wait_event(start)
-    chunks = [(z0, min(z0 + C, nz)) for z0 in range(0, nz, C)]
-    if len(chunks) > 1 and chunks[-1][1] - chunks[-1][0] < r:
-        # a last chunk thinner than the halo cannot serve its predecessor: merge it
-        chunks[-2:] = [(chunks[-2][0], nz)]
-        grow = chunks[-1][1] - chunks[-1][0] - C
-        ibuf = [torch.empty((C + grow + 2 * r, ny, nx), dtype=x.dtype, device=dev) for _ in range(NB)]
-        obuf = [torch.empty((C + grow, ny, nx), dtype=x.dtype, device=dev) for _ in range(NB)]
     n = len(chunks)
 
     def load(i):
