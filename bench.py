@@ -196,13 +196,15 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
-        step()
-    barrier()
-
+    # the clock sampler (an nvidia-smi child polling every 200 ms) starts BEFORE the warm-up: its process
+    # start-up and NVML initialisation otherwise land inside the few-millisecond timed region and perturb it
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+        time.sleep(0.5)
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
     _ffi.LAUNCHES = 0
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
