@@ -702,8 +702,14 @@ def gaussian_gradient_magnitude(input, sigma, output=None, mode="reflect", cval=
     ndim = inp.ndim
     dtype_mode = _check_dtype_mode(kwargs.get("dtype_mode"))
     truncate = kwargs.get("truncate", 4.0)
+    # a mode SEQUENCE means "mode[a] for every pass of the derivative along axis a" (filters.py:1175-1201:
+    # derivative(input, axis, output, modes[axis], ...)), not one mode per filtered axis: only a single mode
+    # maps onto the fused launches, whose smoothing and derivative passes share one mode per filtered axis
+    modes = _normalize_sequence(mode, ndim)
+    single_mode = all(m == modes[0] for m in modes)
     if set(kwargs) <= {"dtype_mode", "truncate"} and dtype_mode != "ndimage" and inp.dtype == _F32 \
-            and ndim in (2, 3) and inp.size:
+            and ndim in (2, 3) and inp.size and single_mode:
+        mode = modes[0]
         out, _ = _get_output(output, inp)
         if out.dtype == _F32:
             smooth = _gaussian_specs(inp, sigma, 0, mode, truncate)

@@ -170,6 +170,9 @@ class ZSlabFilter:
         if output is None:
             output = torch.empty_like(x)
         if compute is None:
+            if not isinstance(self.mode, str):
+                raise ValueError("sharded gradient magnitude takes a single boundary mode (a sequence means one "
+                                 "mode per DERIVATIVE axis, filters.py:1175-1201)")
             inp = _array.ingest(x)
             smooth = _filters._gaussian_specs(inp, sigma, 0, self.mode, truncate)
             deriv = _filters._gaussian_specs(inp, sigma, 1, self.mode, truncate)

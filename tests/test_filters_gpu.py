@@ -479,3 +479,20 @@ def test_f32_streaming_single_axis_passes(mode, ndi):
         out = torch.empty((n, 24, 64), dtype=torch.float32, device="cuda")
         F._launch_pass(_array.ingest(xd), _array.ingest(out), spec, 0.75, False, in_offset=off)
         np.testing.assert_array_equal(to_host(out), full[off:off + n])
+
+
+def test_gradient_magnitude_mode_sequence(ndi):
+    """mode=[m0, m1, m2] means: the derivative along axis a is a full Gaussian filter with mode m_a on EVERY
+    axis (reference filters.py:1175-1201), not one mode per filtered axis."""
+    rng = np.random.default_rng(51)
+    for shape in [(26, 60, 100), (40, 64)]:
+        x = rng.random(shape).astype(np.float32)
+        xd = to_device(x)
+        for mode in (["constant", "mirror", "nearest"][:len(shape)], ["wrap", "reflect", "constant"][:len(shape)],
+                     ["nearest"] * len(shape), "mirror"):
+            want = oracle.gaussian_gradient_magnitude(x, 1.5, mode=mode)
+            got = to_host(ndi.gaussian_gradient_magnitude(xd, 1.5, mode=mode))
+            assert_f32_close(got, want, atol=2e-6)
+            want = oracle.gaussian_laplace(x, 1.5, mode=mode)
+            got = to_host(ndi.gaussian_laplace(xd, 1.5, mode=mode))
+            assert_f32_close(got, want, atol=2e-6)
