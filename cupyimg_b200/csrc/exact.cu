@@ -10,6 +10,7 @@
 // Replaces one launch of the reference's generated ElementwiseKernel
 // (_filters_core.py:190-348, body in SURVEY.md App. A).  Unlike that kernel the
 // boundary rule is evaluated only for threads whose window leaves the array.
+#include <cmath>
 #include <type_traits>
 #include "common.cuh"
 #include "kernels.h"
@@ -80,9 +81,72 @@ exact_corr1d_kernel(const __grid_constant__ ExactParams p)
     }
 }
 
+// uniform_filter1d with scipy's running sum, one thread per line:
+//     tmp = sum of the first window;  out[0] = tmp / K;  tmp += x[l + K - 1] - x[l - 1];  out[l] = tmp / K
+// The window-sum kernel above gives the same bits whenever every partial sum is exact (integer data, integer
+// cval).  It does not when the sums round — float input, or constant mode with a fractional cval — and the
+// output is an integer type, where one ulp can flip a truncation; those calls take this sequential kernel.
+template <typename InT>
+__global__ void __launch_bounds__(128)
+uniform_running_kernel(const __grid_constant__ ExactParams p, const int64_t lines)
+{
+    const int K = p.K;
+    const int64_t astride = p.istride[p.axis], ostr = p.ostride[p.axis], n_out = p.shape[p.axis];
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t ln = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; ln < lines; ln += stride) {
+        int64_t rem = ln, ioff = 0, ooff = 0;
+#pragma unroll 1
+        for (int d = p.ndim - 1; d >= 0; --d) {
+            if (d == p.axis) continue;
+            const int64_t ext = p.shape[d];
+            const int64_t c = rem % ext;
+            rem /= ext;
+            ioff += c * p.istride[d];
+            ooff += c * p.ostride[d];
+        }
+        const char* line = p.in + ioff;
+        const int64_t first = p.in_offset - p.before;            // source index of extended element 0
+        auto ext_at = [&](int64_t l) -> double {
+            const int64_t src = remap_index(p.mode, first + l, p.n_in);
+            return src < 0 ? p.cval : load_as_double<InT>(line + src * astride);
+        };
+        double tmp = 0.0;
+        for (int l = 0; l < K; ++l) tmp = __dadd_rn(tmp, ext_at(l));
+        store_cast(p.out + ooff, p.out_dtype, __ddiv_rn(tmp, (double)K));
+        for (int64_t l = 1; l < n_out; ++l) {
+            tmp = __dadd_rn(tmp, __dsub_rn(ext_at(l + K - 1), ext_at(l - 1)));
+            store_cast(p.out + ooff + l * ostr, p.out_dtype, __ddiv_rn(tmp, (double)K));
+        }
+    }
+}
+
+static bool needs_running_sum(const ExactParams& p)
+{
+    if (p.symmetric != 2) return false;
+    if (p.out_dtype == SEPFILT_F32 || p.out_dtype == SEPFILT_F64) return false;   // float outputs: rtol contract
+    if (p.in_dtype == SEPFILT_F32 || p.in_dtype == SEPFILT_F64) return true;
+    return p.mode == SEPFILT_CONSTANT && p.cval != floor(p.cval);
+}
+
 cudaError_t launch_exact_corr1d(const ExactParams& p, cudaStream_t s)
 {
     if (p.total <= 0) return cudaSuccess;
+    if (needs_running_sum(p)) {
+        const int64_t lines = p.total / p.shape[p.axis];
+        int64_t b64 = (lines + 127) / 128;
+        const int blocks = (int)(b64 < 148 * 16 ? b64 : 148 * 16);
+        switch (p.in_dtype) {
+#define CASE(T, C) case T: uniform_running_kernel<C><<<blocks, 128, 0, s>>>(p, lines); break;
+            CASE(SEPFILT_I8, int8_t) CASE(SEPFILT_U8, uint8_t) CASE(SEPFILT_BOOL, uint8_t)
+            CASE(SEPFILT_I16, int16_t) CASE(SEPFILT_U16, uint16_t)
+            CASE(SEPFILT_I32, int32_t) CASE(SEPFILT_U32, uint32_t)
+            CASE(SEPFILT_I64, int64_t) CASE(SEPFILT_U64, uint64_t)
+            CASE(SEPFILT_F32, float) CASE(SEPFILT_F64, double)
+#undef CASE
+        default: return cudaErrorInvalidValue;
+        }
+        return cudaGetLastError();
+    }
     const int threads = 256;
     int64_t blocks64 = (p.total + threads - 1) / threads;
     const int64_t cap = 148 * 32;   // grid-stride beyond 32 CTAs per SM

@@ -496,3 +496,23 @@ def test_gradient_magnitude_mode_sequence(ndi):
             want = oracle.gaussian_laplace(x, 1.5, mode=mode)
             got = to_host(ndi.gaussian_laplace(xd, 1.5, mode=mode))
             assert_f32_close(got, want, atol=2e-6)
+
+
+def test_uniform_integer_output_inexact_sums(ndi):
+    """Integer outputs stay bit-exact where the window sums round (constant mode with a fractional cval, float
+    input): those calls follow scipy's running sum along the line, found by the fuzz test."""
+    rng = np.random.default_rng(77)
+    x = rng.integers(0, 30000, (32, 53, 256)).astype(np.uint32)
+    xd = to_device(x)
+    for size, origin in [(3, 0), (6, -1), ([2, 5, 4], 0)]:
+        want = oracle.uniform_filter(x, size, mode="constant", cval=7.7, origin=origin)
+        got = to_host(ndi.uniform_filter(xd, size, mode="constant", cval=7.7, origin=origin))
+        np.testing.assert_array_equal(got, want)
+    xf = (rng.standard_normal((40, 300)) * 1000).astype(np.float32)
+    for t_out in ("int16", "int32", "uint8"):
+        want = oracle.uniform_filter(xf, 5, output=np.dtype(t_out), mode="mirror")
+        got = to_host(ndi.uniform_filter(to_device(xf), 5, output=np.dtype(t_out), mode="mirror", dtype_mode="ndimage"))
+        np.testing.assert_array_equal(got, want)
+    want = oracle.uniform_filter1d(x, 7, axis=1, mode="constant", cval=-0.3)
+    got = to_host(ndi.uniform_filter1d(xd, 7, axis=1, mode="constant", cval=-0.3))
+    np.testing.assert_array_equal(got, want)

@@ -18,3 +18,14 @@ def test_random_shapes_and_modes(seed):
         pytest.skip("needs a CUDA device")
     import fuzz_fused
     assert fuzz_fused.run(seed, 70, verbose=False) == 0
+
+
+@pytest.mark.parametrize("seed", [11, 12, 13])
+def test_random_exact_paths_bit_exact(seed):
+    """Integer / float64 arrays through the exact kernels (streaming, tiled, general, min / max, N-d
+    correlate): random dtypes, shapes, modes, cvals, origins — bit for bit against the oracle."""
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    import fuzz_fused
+    assert fuzz_fused.run_exact(seed, 80, verbose=False) == 0
