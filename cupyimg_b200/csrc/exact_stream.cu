@@ -12,11 +12,12 @@
 //       window as float64 in REGISTERS (rotating slots, fully unrolled: no shared memory, no
 //       register moves).  Every element is loaded once per segment and converted once; the rows
 //       of the next 2R+1 steps are in flight while the current ones are filtered.
-//   exact_stream_row_kernel  contiguous axis: raw 16-byte chunks of a row segment (+ halo chunks,
-//       boundary remap _util.py:170-228 resolved per staged halo element only) are staged in shared
-//       memory with vector loads, each thread converts a 16 + 2R window once and produces 16
-//       adjacent outputs, stored as 16-byte vectors.
-// (the row kernel stages nothing in shared memory: see the comment at exact_stream_row_kernel)
+//   exact_stream_row_kernel  contiguous axis: a thread loads the 16-byte chunks of its 16 outputs plus
+//       the halo chunks on either side straight from global memory (its neighbours' chunks: L1 hits),
+//       converts the 16 + 2R window once, and stores 16-byte vectors.  On aligned rows the halo of a
+//       row's first / last thread is filled by register selects from elements the thread already
+//       holds; otherwise element-wise through the boundary rule (_util.py:170-228).
+// Neither kernel uses shared memory or a CTA barrier.
 // Out-of-range float64 -> integer casts follow x86 cvttsd2si ("integer indefinite"), detected
 // with an integer compare on the exponent instead of FP64 compares.
 #include "common.cuh"
