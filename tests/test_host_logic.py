@@ -92,3 +92,39 @@ def test_dtype_helpers():
         _array.ingest(np.zeros(3))
     with pytest.raises(TypeError):
         _array.ingest(torch.zeros(3))
+
+
+def test_complex_views_and_output_rules():
+    """Complex arrays are filtered by component: strided float views of the same memory; a complex input or
+    complex weights need a complex output (_util.py:52-75)."""
+    c = _fake(4096, (3, 5), (40, 8), "complex64")
+    re, im = c.component(0), c.component(1)
+    assert re.dtype == np.dtype("float32") and im.dtype == np.dtype("float32")
+    assert (re.ptr, im.ptr) == (4096, 4100) and re.strides == im.strides == (40, 8)
+    assert not re.c_contiguous() and re.may_overlap(im)         # interleaved: byte ranges overlap
+    z = _fake(0, (2,), (16,), "complex128")
+    assert z.component(1).ptr == 8 and z.component(1).dtype == np.dtype("float64")
+    with pytest.raises(TypeError):
+        _fake(0, (2,), (4,), "float32").component(0)
+    with pytest.raises(RuntimeError):
+        F._get_output(np.float32, c)                            # complex input, real output dtype
+    with pytest.raises(RuntimeError):
+        F._get_output(np.float64, _fake(0, (2, 2), (8, 4)), complex_output=True)   # complex weights
+    assert F._split_cval(1.5, False) == (1.5, 0.0)
+    assert F._split_cval(1.5 - 2j, True) == (1.5, -2.0)
+    with pytest.raises(ValueError):
+        F._split_cval(1j, False)
+
+
+def test_window_filter_specs():
+    """minimum / maximum passes never take the float32 tiled or fused paths (exact per-axis kernels)."""
+    a = _fake(1024, (8, 16, 32), (2048, 128, 4))
+    b = _fake(1 << 20, (8, 16, 32), (2048, 128, 4))
+    mx = F._PassSpec(1, None, 0, 0, uniform=F._MAX, size=5)
+    mean = F._PassSpec(1, None, 0, 0, uniform=True, size=5)
+    assert mx.radius() == 2 and mx.struct()[0].uniform == 3 and mean.struct()[0].uniform == 1
+    assert F._f32_tiled_ok(a, b, mean) and not F._f32_tiled_ok(a, b, mx)
+    assert F._fused_candidate(a, b, [mean, F._PassSpec(2, None, 0, 0, uniform=True, size=3)], False)
+    assert not F._fused_candidate(a, b, [mx, F._PassSpec(2, None, 0, 0, uniform=F._MAX, size=3)], False)
+    with pytest.raises(NotImplementedError):
+        F._check_minmax_cval(float("nan"))
