@@ -353,7 +353,9 @@ static int build_fused(const sepfilt_tensor* in, const sepfilt_tensor* out,
     v->ny = (int32_t)in->shape[nd - 2];
     v->nx = (int32_t)in->shape[nd - 1];
     v->cval = (float)cval;
-    if (!fused3d_supported(*v, taps, gradient_magnitude != 0)) UNSUP("geometry not supported by the fused kernel");
+    if (!fused_ws_supported(*v, taps, dtaps, gradient_magnitude != 0) &&
+        !fused3d_supported(*v, taps, gradient_magnitude != 0))
+        UNSUP("geometry not supported by the fused kernel");
     return SEPFILT_OK;
 #undef UNSUP
 }
@@ -380,8 +382,11 @@ int sepfilt_separable_f32(const sepfilt_tensor* in, const sepfilt_tensor* out,
     if (numel(out) == 0) return SEPFILT_OK;
     DeviceGuard guard(in->device);
     if (guard.err != cudaSuccess) return fail_cuda(guard.err, "cudaSetDevice");
-    cudaError_t e = launch_fused3d(v, taps, dtaps, gradient_magnitude != 0, static_cast<cudaStream_t>(stream));
-    if (e != cudaSuccess) return fail_cuda(e, "fused3d launch");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    cudaError_t e = fused_ws_supported(v, taps, dtaps, gradient_magnitude != 0)
+                        ? launch_fused_ws(v, taps, dtaps, gradient_magnitude != 0, s)
+                        : launch_fused3d(v, taps, dtaps, gradient_magnitude != 0, s);
+    if (e != cudaSuccess) return fail_cuda(e, "fused launch");
     return SEPFILT_OK;
 }
 

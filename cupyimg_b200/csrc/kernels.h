@@ -105,4 +105,9 @@ bool        fused3d_supported(const FusedVolume& v, const F32Taps taps[3], bool 
 cudaError_t launch_fused3d(const FusedVolume& v, const F32Taps taps[3], const F32Taps dtaps[3],
                            bool gradmag, cudaStream_t s);
 
+// ---- warp-specialised fused f32 (fused_ws.cu): same contract as fused3d, tried first ----
+bool        fused_ws_supported(const FusedVolume& v, const F32Taps taps[3], const F32Taps dtaps[3], bool gradmag);
+cudaError_t launch_fused_ws(const FusedVolume& v, const F32Taps taps[3], const F32Taps dtaps[3],
+                            bool gradmag, cudaStream_t s);
+
 }  // namespace sepfilt
