@@ -59,6 +59,7 @@ class Pass(ctypes.Structure):
 EXPORTS = (
     "sepfilt_version", "sepfilt_last_error", "sepfilt_correlate1d", "sepfilt_separable_f32",
     "sepfilt_separable_f32_supported", "sepfilt_gradmag_step", "sepfilt_copy_cast", "sepfilt_correlate_nd",
+    "sepfilt_last_launch_count",
 )
 
 _lib = None
@@ -95,6 +96,7 @@ def lib():
         L.sepfilt_separable_f32.restype = ci
         L.sepfilt_separable_f32_supported.argtypes = [TP, TP, PP, ci, ci, dbl]
         L.sepfilt_separable_f32_supported.restype = ci
+        L.sepfilt_last_launch_count.restype = ci
         L.sepfilt_gradmag_step.argtypes = [vp, vp, i64, ci, ci, vp]
         L.sepfilt_gradmag_step.restype = ci
         i32p = ctypes.POINTER(ctypes.c_int32)

@@ -17,6 +17,7 @@ using namespace sepfilt;
 namespace {
 
 thread_local std::string g_last_error;
+thread_local int g_last_launches = 0;     // kernels enqueued by the last sepfilt_separable_f32 call of this thread
 
 int fail(int code, const char* fmt, ...)
 {
@@ -383,12 +384,16 @@ int sepfilt_separable_f32(const sepfilt_tensor* in, const sepfilt_tensor* out,
     DeviceGuard guard(in->device);
     if (guard.err != cudaSuccess) return fail_cuda(guard.err, "cudaSetDevice");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    cudaError_t e = fused_ws_supported(v, taps, dtaps, gradient_magnitude != 0)
-                        ? launch_fused_ws(v, taps, dtaps, gradient_magnitude != 0, s)
-                        : launch_fused3d(v, taps, dtaps, gradient_magnitude != 0, s);
+    const bool ws = fused_ws_supported(v, taps, dtaps, gradient_magnitude != 0);
+    cudaError_t e = ws ? launch_fused_ws(v, taps, dtaps, gradient_magnitude != 0, s)
+                       : launch_fused3d(v, taps, dtaps, gradient_magnitude != 0, s);
     if (e != cudaSuccess) return fail_cuda(e, "fused launch");
+    // the warp-specialised kernel computes the gradient magnitude in one launch, fused3d in one per axis
+    g_last_launches = (gradient_magnitude && !ws) ? in->ndim : 1;
     return SEPFILT_OK;
 }
+
+int sepfilt_last_launch_count(void) { return g_last_launches; }
 
 int sepfilt_gradmag_step(void* acc, const void* a, int64_t n, int dtype, int op, void* stream)
 {

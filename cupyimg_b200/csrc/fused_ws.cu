@@ -59,9 +59,11 @@ __host__ __device__ constexpr int cmin(int a, int b) { return a < b ? a : b; }
 
 // R: radius (exact), CPT: columns per XZ thread (8: 16 threads per tile row, 4: 32), TYC: tile rows,
 // HAS_Z: z pass present, GRAD: gradient magnitude (2 y-filtered planes, 3 z accumulator sets)
-template <int R_, int CPT_, int TYC_, bool HAS_Z_, bool GRAD_, int YREGS_, int XZREGS_>
+// YSPLIT: the Y warps filter the tile rows in this many chunks (fewer live accumulators, more row loads)
+template <int R_, int CPT_, int TYC_, bool HAS_Z_, bool GRAD_, int YREGS_, int XZREGS_, int YSPLIT_ = 1>
 struct WsCfg {
-    static constexpr int R = R_, CPT = CPT_, TYC = TYC_, YREGS = YREGS_, XZREGS = XZREGS_;
+    static constexpr int R = R_, CPT = CPT_, TYC = TYC_, YREGS = YREGS_, XZREGS = XZREGS_, YSPLIT = YSPLIT_;
+    static constexpr int YCH = TYC_ / YSPLIT_;                  // rows per chunk
     static constexpr bool HAS_Z = HAS_Z_, GRAD = GRAD_;
     static constexpr int TX = 128, TPR = TX / CPT;
     static constexpr int NT = 384, NYW = 4;
@@ -90,7 +92,10 @@ struct WsCfg {
     static_assert(NR >= 5, "too few raw slots");
     static_assert(NY % G == 0, "slot arithmetic assumes NY % G == 0");
     static_assert(NXZW <= 8 && NXZW >= 1, "XZ warps");
-    static_assert(NYW * YREGS_ * 32 + 8 * XZREGS_ * 32 <= 65536, "register file");
+    // setmaxnreg moves registers inside the CTA's launch allocation: 12 warps x 168 (= 65536 / 384 rounded
+    // down to 8); a budget beyond it makes setmaxnreg.inc wait forever
+    static_assert(NYW * YREGS_ + 8 * XZREGS_ <= 12 * 168, "register budget exceeds the launch allocation");
+    static_assert(TYC_ % YSPLIT_ == 0, "row chunks");
     static_assert(WS_SMEM_BUDGET >= (int)SMEM, "shared memory");
 };
 
@@ -207,15 +212,17 @@ fws_kernel(const __grid_constant__ WsParams p, const __grid_constant__ CUtensorM
                 __syncwarp();
             }
             mbar_wait(&empty_y[ys], ((uint32_t)(pl / NY) & 1u) ^ 1u);
-            // ---- main part: lane owns staged columns [4 lane, 4 lane + 4), all TYC rows
-            {
-                u64 acc[NF][TYC][2];
-                const float* src = rawp + 4 * lane;
+            // ---- main part: lane owns staged columns [4 lane, 4 lane + 4), all TYC rows (YSPLIT chunks)
 #pragma unroll
-                for (int j = 0; j < TYC + 2 * R; ++j) {
+            for (int h = 0; h < C::YSPLIT; ++h) {
+                constexpr int YCH = C::YCH;
+                u64 acc[NF][YCH][2];
+                const float* src = rawp + 4 * lane + h * YCH * PW;
+#pragma unroll
+                for (int j = 0; j < YCH + 2 * R; ++j) {
                     const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(src + j * PW);
 #pragma unroll
-                    for (int o = 0; o < TYC; ++o) {
+                    for (int o = 0; o < YCH; ++o) {
                         const int k = j - o;
                         if (k == 0) {                          // first tap initialises: no zeroing
                             acc[0][o][0] = mul2s(v.x, p.wy[0]);
@@ -231,11 +238,11 @@ fws_kernel(const __grid_constant__ WsParams p, const __grid_constant__ CUtensorM
                         }
                     }
                 }
-                float* dst = yp + ycol_offset<SWZ, C::ODD_OFF>(4 * lane);
+                float* dst = yp + ycol_offset<SWZ, C::ODD_OFF>(4 * lane) + h * YCH * YP;
 #pragma unroll
                 for (int f = 0; f < NF; ++f)
 #pragma unroll
-                    for (int o = 0; o < TYC; ++o)
+                    for (int o = 0; o < YCH; ++o)
                         *reinterpret_cast<ulonglong2*>(dst + (f * TYC + o) * YP) = make_ulonglong2(acc[f][o][0], acc[f][o][1]);
             }
             // ---- tail: staged columns [128, 128 + 2 HL): lane = (column pair, row part)
@@ -517,18 +524,32 @@ cudaError_t launch_plain(const FusedVolume& v, WsParams& p, int sms, cudaStream_
     return launch_cfg<WsCfg<R, 8, 16, HAS_Z, false, 104, 200>>(v, p, p16, s);
 }
 
+// gradient magnitude: 4 columns per XZ thread, 8 tile rows (three z accumulator sets per column)
+template <int R>
+cudaError_t launch_grad(const FusedVolume& v, WsParams& p, int sms, cudaStream_t s)
+{
+    const WsPlan plan = plan_tiles(v, R, true, 8, sms);
+    return launch_cfg<WsCfg<R, 4, 8, true, true, 72, 216, 2>>(v, p, plan, s);
+}
+
 }  // namespace
 
 bool fused_ws_supported(const FusedVolume& v, const F32Taps taps[3], const F32Taps dtaps[3], bool gradmag)
 {
     if (getenv("SEPFILT_NO_WS")) return false;                  // A/B aid
-    if (!getenv("SEPFILT_WS")) return false;                    // opt-in until it beats fused3d in every mode
     const bool has_z = !(taps[0].radius == 0 && taps[0].w[0] == 1.0f);
     const int r = taps[2].radius;
     if (taps[1].radius != r || (has_z && taps[0].radius != r)) return false;   // one exact radius for all axes
-    if (gradmag) return false;                                  // (instantiated below when enabled)
-    if (r != 8 || !has_z) return false;
-    (void)dtaps;
+    if (gradmag) {
+        // one launch for the whole gradient magnitude: three z accumulator sets per column fit the
+        // register file up to radius 6 (sigma <= 1.5 at truncate 4)
+        if (!has_z || r < 1 || r > 6) return false;
+        for (int a = 0; a < 3; ++a)
+            if (dtaps[a].radius != r) return false;
+    } else {
+        if (!getenv("SEPFILT_WS")) return false;                // plain filters: opt-in until it beats fused3d in every mode
+        if (r != 8 || !has_z) return false;
+    }
     if (v.nx % 4 != 0 || (reinterpret_cast<uintptr_t>(v.in) & 15) || (reinterpret_cast<uintptr_t>(v.out) & 15))
         return false;
     if (v.nx < 16 || v.ny < r + 1 || v.nx < r + 1 || v.nz_in < 1 || v.nz_out < 1) return false;
@@ -553,6 +574,17 @@ cudaError_t launch_fused_ws(const FusedVolume& v, const F32Taps taps[3], const F
     put_taps(taps[0], p.wz); put_taps(taps[1], p.wy); put_taps(taps[2], p.wx);
     if (gradmag) { put_taps(dtaps[0], p.dz); put_taps(dtaps[1], p.dy); put_taps(dtaps[2], p.dx); }
     const int sms = device_sms();
+    if (gradmag) {
+        switch (taps[2].radius) {
+        case 1: return launch_grad<1>(v, p, sms, s);
+        case 2: return launch_grad<2>(v, p, sms, s);
+        case 3: return launch_grad<3>(v, p, sms, s);
+        case 4: return launch_grad<4>(v, p, sms, s);
+        case 5: return launch_grad<5>(v, p, sms, s);
+        case 6: return launch_grad<6>(v, p, sms, s);
+        default: return cudaErrorInvalidValue;
+        }
+    }
     return launch_plain<8, true>(v, p, sms, s);
 }
 

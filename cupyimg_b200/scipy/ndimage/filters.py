@@ -243,7 +243,7 @@ def _try_fused(inp, out, specs, cval, dspecs=None, in_offset0=0):
     if rc == _ffi.ERR_UNSUPPORTED:
         return False
     _ffi.check(rc)
-    _ffi.count_launch(1 if dspecs is None else len(structs))
+    _ffi.count_launch(_ffi.lib().sepfilt_last_launch_count())
     return True
 
 

@@ -148,6 +148,11 @@ SEPFILT_API int sepfilt_separable_f32(const sepfilt_tensor* in, const sepfilt_te
                           const sepfilt_pass* dpasses, int gradient_magnitude,
                           int64_t in_offset0, double cval, void* stream);
 
+/* Kernels enqueued by the calling thread's last successful sepfilt_separable_f32 call (1, or one per
+ * axis when the gradient magnitude runs as accumulating launches): lets the host layer report
+ * launch counts instead of assuming them. */
+SEPFILT_API int sepfilt_last_launch_count(void);
+
 /* Would sepfilt_separable_f32 accept this request?  1 yes, 0 no (no error is set). */
 SEPFILT_API int sepfilt_separable_f32_supported(const sepfilt_tensor* in, const sepfilt_tensor* out,
                                     const sepfilt_pass* passes, int npasses,
