@@ -334,16 +334,31 @@ fws_kernel(const __grid_constant__ WsParams p, const __grid_constant__ CUtensorM
             }
         }
     };
-    auto xpass = [&](const float (&win)[WIN], const float* w, u64 (&o)[NP]) {
-        float xo[CPT];
+    // x pass on packed column pairs (FFMA2): output pair j needs the input pairs starting at window index
+    // 2j + (HL - R) + k; even starts are the aligned pairs of the window, odd starts are re-paired copies
+    // (two MOVs each, once per window, shared by every tap set) — half the issue slots of a scalar FFMA pass,
+    // same products, same summation order
+    auto pair_window = [&](const float (&win)[WIN], u64 (&pe)[WIN / 2], u64 (&po)[WIN / 2]) {
 #pragma unroll
-        for (int c = 0; c < CPT; ++c) xo[c] = w[0] * win[c + HL - R];
+        for (int m = 0; m < WIN / 2; ++m) pe[m] = pack2(win[2 * m], win[2 * m + 1]);
+#pragma unroll
+        for (int m = 0; m + 1 < WIN / 2; ++m) po[m] = pack2(win[2 * m + 1], win[2 * m + 2]);
+        po[WIN / 2 - 1] = 0ull;
+    };
+    auto xpass = [&](const u64 (&pe)[WIN / 2], const u64 (&po)[WIN / 2], const float* w, u64 (&o)[NP]) {
+#pragma unroll
+        for (int j = 0; j < NP; ++j) {
+            constexpr int off = HL - R;
+            const int i0 = 2 * j + off;
+            o[j] = mul2s((i0 & 1) ? po[i0 >> 1] : pe[i0 >> 1], w[0]);
+        }
 #pragma unroll
         for (int k = 1; k <= 2 * R; ++k)
 #pragma unroll
-            for (int c = 0; c < CPT; ++c) xo[c] = fmaf(w[k], win[c + HL - R + k], xo[c]);
-#pragma unroll
-        for (int c = 0; c < NP; ++c) o[c] = pack2(xo[2 * c], xo[2 * c + 1]);
+            for (int j = 0; j < NP; ++j) {
+                const int i = 2 * j + (HL - R) + k;
+                o[j] = fma2s((i & 1) ? po[i >> 1] : pe[i >> 1], w[k], o[j]);
+            }
     };
     // shifting z accumulators (see fused3d.cu): 2R+1 logical accumulators in 2R+1 + (G-1) slots; inside a
     // G-plane group every update is in place, the last plane of a group writes logical j back to slot j
@@ -372,20 +387,24 @@ fws_kernel(const __grid_constant__ WsParams p, const __grid_constant__ CUtensorM
             u64 v[NZF][NP];
             {
                 float win[WIN];
+                u64 pe[WIN / 2], po[WIN / 2];
                 load_window(yp, win);
+                pair_window(win, pe, po);
                 if (!GRAD) {
-                    xpass(win, p.wx, v[0]);
+                    xpass(pe, po, p.wx, v[0]);
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&empty_y[ys]);   // after the x pass: every lane's window is in registers
                 } else {
-                    xpass(win, p.wx, v[0]);                    // Gy Gx   -> z derivative term
-                    xpass(win, p.dx, v[NZF - 1]);              // Gy G'x  -> x term
+                    xpass(pe, po, p.wx, v[0]);                 // Gy Gx   -> z derivative term
+                    xpass(pe, po, p.dx, v[NZF - 1]);           // Gy G'x  -> x term
                 }
             }
             if (GRAD) {
                 float win[WIN];
+                u64 pe[WIN / 2], po[WIN / 2];
                 load_window(yp + TYC * YP, win);
-                xpass(win, p.wx, v[NZF > 1 ? 1 : 0]);          // G'y Gx  -> y term
+                pair_window(win, pe, po);
+                xpass(pe, po, p.wx, v[NZF > 1 ? 1 : 0]);       // G'y Gx  -> y term
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&empty_y[ys]);
             }
