@@ -56,10 +56,23 @@ class Pass(ctypes.Structure):
     ]
 
 
+class Halo(ctypes.Structure):
+    _fields_ = [
+        ("lo", ctypes.c_void_p),
+        ("hi", ctypes.c_void_p),
+        ("planes_lo", ctypes.c_int32),
+        ("planes_hi", ctypes.c_int32),
+        ("ready_lo", ctypes.c_void_p),
+        ("ready_hi", ctypes.c_void_p),
+        ("epoch", ctypes.c_uint32),
+        ("reserved", ctypes.c_uint32),
+    ]
+
+
 EXPORTS = (
     "sepfilt_version", "sepfilt_last_error", "sepfilt_correlate1d", "sepfilt_separable_f32",
     "sepfilt_separable_f32_supported", "sepfilt_gradmag_step", "sepfilt_copy_cast", "sepfilt_correlate_nd",
-    "sepfilt_last_launch_count",
+    "sepfilt_last_launch_count", "sepfilt_separable_f32_halo", "sepfilt_stream_write32", "sepfilt_stream_wait32_geq",
 )
 
 _lib = None
@@ -97,6 +110,12 @@ def lib():
         L.sepfilt_separable_f32_supported.argtypes = [TP, TP, PP, ci, ci, dbl]
         L.sepfilt_separable_f32_supported.restype = ci
         L.sepfilt_last_launch_count.restype = ci
+        L.sepfilt_separable_f32_halo.argtypes = [TP, TP, PP, ci, PP, ci, ctypes.POINTER(Halo), dbl, vp]
+        L.sepfilt_separable_f32_halo.restype = ci
+        L.sepfilt_stream_write32.argtypes = [vp, vp, ctypes.c_uint32]
+        L.sepfilt_stream_write32.restype = ci
+        L.sepfilt_stream_wait32_geq.argtypes = [vp, vp, ctypes.c_uint32]
+        L.sepfilt_stream_wait32_geq.restype = ci
         L.sepfilt_gradmag_step.argtypes = [vp, vp, i64, ci, ci, vp]
         L.sepfilt_gradmag_step.restype = ci
         i32p = ctypes.POINTER(ctypes.c_int32)

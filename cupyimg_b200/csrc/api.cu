@@ -1,6 +1,7 @@
 // api.cu — the extern "C" boundary declared in include/sepfilt.h: argument validation,
 // geometry normalisation and kernel dispatch.  No device allocation, no retained
 // pointers, all launches on the caller's stream.
+#include <cuda.h>
 #include <cfloat>
 #include <cmath>
 #include <cstdarg>
@@ -300,7 +301,8 @@ int sepfilt_correlate1d(const sepfilt_tensor* in, const sepfilt_tensor* out,
 static int build_fused(const sepfilt_tensor* in, const sepfilt_tensor* out,
                        const sepfilt_pass* passes, int npasses, const sepfilt_pass* dpasses,
                        int gradient_magnitude, int64_t in_offset0, double cval,
-                       FusedVolume* v, F32Taps taps[3], F32Taps dtaps[3], bool set_error)
+                       FusedVolume* v, F32Taps taps[3], F32Taps dtaps[3], bool set_error,
+                       const sepfilt_halo* halo = nullptr)
 {
 #define UNSUP(...) return set_error ? fail(SEPFILT_ERR_UNSUPPORTED, __VA_ARGS__) : SEPFILT_ERR_UNSUPPORTED
     if (!in || !out || !passes) UNSUP("NULL argument");
@@ -354,6 +356,13 @@ static int build_fused(const sepfilt_tensor* in, const sepfilt_tensor* out,
     v->ny = (int32_t)in->shape[nd - 2];
     v->nx = (int32_t)in->shape[nd - 1];
     v->cval = (float)cval;
+    v->halo = halo;
+    if (halo) {
+        if (nd != 3) UNSUP("neighbour halos need a rank-3 slab");
+        if (halo->planes_lo < 0 || halo->planes_hi < 0) UNSUP("negative halo plane count");
+        if ((halo->lo && (reinterpret_cast<uintptr_t>(halo->lo) & 15)) || (halo->hi && (reinterpret_cast<uintptr_t>(halo->hi) & 15)))
+            UNSUP("halo planes must be 16-byte aligned");
+    }
     if (!fused_ws_supported(*v, taps, dtaps, gradient_magnitude != 0) &&
         !fused3d_supported(*v, taps, gradient_magnitude != 0))
         UNSUP("geometry not supported by the fused kernel");
@@ -394,6 +403,60 @@ int sepfilt_separable_f32(const sepfilt_tensor* in, const sepfilt_tensor* out,
 }
 
 int sepfilt_last_launch_count(void) { return g_last_launches; }
+
+int sepfilt_separable_f32_halo(const sepfilt_tensor* in, const sepfilt_tensor* out,
+                               const sepfilt_pass* passes, int npasses,
+                               const sepfilt_pass* dpasses, int gradient_magnitude,
+                               const sepfilt_halo* halo, double cval, void* stream)
+{
+    if (!halo) return fail(SEPFILT_ERR_INVALID, "halo descriptor is NULL");
+    FusedVolume v;
+    F32Taps taps[3], dtaps[3];
+    int rc = build_fused(in, out, passes, npasses, dpasses, gradient_magnitude, 0, cval, &v, taps, dtaps, true, halo);
+    if (rc != SEPFILT_OK) return rc;
+    if (numel(out) == 0) return SEPFILT_OK;
+    DeviceGuard guard(in->device);
+    if (guard.err != cudaSuccess) return fail_cuda(guard.err, "cudaSetDevice");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const bool ws = fused_ws_supported(v, taps, dtaps, gradient_magnitude != 0);
+    cudaError_t e = ws ? launch_fused_ws(v, taps, dtaps, gradient_magnitude != 0, s)
+                       : launch_fused3d(v, taps, dtaps, gradient_magnitude != 0, s);
+    if (e != cudaSuccess) return fail_cuda(e, "fused launch (halo)");
+    g_last_launches = 1;
+    return SEPFILT_OK;
+}
+
+namespace {
+typedef CUresult (*StreamValue32Fn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+StreamValue32Fn stream_value_fn(const char* name)
+{
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint(name, &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+        return nullptr;
+    return reinterpret_cast<StreamValue32Fn>(f);
+}
+}  // namespace
+
+int sepfilt_stream_write32(void* stream, void* addr, uint32_t value)
+{
+    static StreamValue32Fn fn = stream_value_fn("cuStreamWriteValue32");
+    if (!fn) return fail(SEPFILT_ERR_CUDA, "cuStreamWriteValue32 is not available");
+    if (!addr || (reinterpret_cast<uintptr_t>(addr) & 3)) return fail(SEPFILT_ERR_INVALID, "flag address must be 4-byte aligned");
+    const CUresult r = fn(static_cast<CUstream>(stream), reinterpret_cast<CUdeviceptr>(addr), value, CU_STREAM_WRITE_VALUE_DEFAULT);
+    if (r != CUDA_SUCCESS) return fail(SEPFILT_ERR_CUDA, "cuStreamWriteValue32 failed (%d)", (int)r);
+    return SEPFILT_OK;
+}
+
+int sepfilt_stream_wait32_geq(void* stream, void* addr, uint32_t value)
+{
+    static StreamValue32Fn fn = stream_value_fn("cuStreamWaitValue32");
+    if (!fn) return fail(SEPFILT_ERR_CUDA, "cuStreamWaitValue32 is not available");
+    if (!addr || (reinterpret_cast<uintptr_t>(addr) & 3)) return fail(SEPFILT_ERR_INVALID, "flag address must be 4-byte aligned");
+    const CUresult r = fn(static_cast<CUstream>(stream), reinterpret_cast<CUdeviceptr>(addr), value, CU_STREAM_WAIT_VALUE_GEQ);
+    if (r != CUDA_SUCCESS) return fail(SEPFILT_ERR_CUDA, "cuStreamWaitValue32 failed (%d)", (int)r);
+    return SEPFILT_OK;
+}
 
 int sepfilt_gradmag_step(void* acc, const void* a, int64_t n, int dtype, int op, void* stream)
 {

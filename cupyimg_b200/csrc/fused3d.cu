@@ -24,9 +24,11 @@
 #include <cuda.h>
 #include <cstddef>
 #include <cstdlib>
+#include <cstring>
 
 #include "common.cuh"
 #include "kernels.h"
+#include "ptx.cuh"
 
 namespace sepfilt {
 
@@ -79,7 +81,7 @@ template <int R, int TX_, int G_, int CTAS_, int RY_ = 8> struct Cfg {
     static constexpr int ITEMS = 2 * NCG * G;          // y-pass items (4 cols x RY rows) per group
     static constexpr int MAXCELL = RROWS * 2 * HL;     // out-of-array column cells of one plane slot
     // raw[2][G][RSLOT] + ybuf[2][G][YSLOT] + patch tables (cells + rows) + 3 mbarriers + patch parameters
-    static constexpr size_t SMEM = sizeof(float) * (2 * (size_t)G * (RSLOT + YSLOT)) + sizeof(int) * ((MAXCELL + RROWS + 1) & ~1) + 80;
+    static constexpr size_t SMEM = sizeof(float) * (2 * (size_t)G * (RSLOT + YSLOT)) + sizeof(int) * ((MAXCELL + RROWS + 1) & ~1) + 96;
     static_assert(ITEMS <= NT, "one y-pass item per thread");
 };
 
@@ -141,6 +143,14 @@ __device__ __forceinline__ void tma_load_plane(void* dst, const CUtensorMap* map
         : "memory");
 }
 
+// wait (one thread, once per CTA, before the plane loop) until both neighbours' slabs are complete
+__device__ __noinline__ void halo_wait_ready(const ptx::HaloMaps& hm)
+{
+    if (hm.planes_lo && hm.ready_lo) ptx::wait_flag_geq(hm.ready_lo, hm.epoch);
+    if (hm.planes_hi && hm.ready_hi) ptx::wait_flag_geq(hm.ready_hi, hm.epoch);
+    ptx::fence_proxy_async_all();
+}
+
 // generic_gradient_magnitude staging in the output dtype (filters.py:1187-1201), fused into the store:
 // 1: out = v*v   2: out += v*v   3: out = sqrt(out + v*v); explicit _rn ops, no FMA contraction, so
 // the float32 roundings are the ones of the reference's separate multiply / add / sqrt kernels.
@@ -169,9 +179,12 @@ __device__ __noinline__ float fetch_remapped_cell(const FusedParams& p, int pz, 
 } __device__ long long g_dbg_cycles[4096]; namespace {
 #endif
 
-template <int R, bool HAS_Z, class C, bool EPI>
+// HALO: the planes beyond the slab's ends come from the neighbours' arrays (multi-GPU z-slabs); a separate
+// instantiation so that the single-GPU kernel keeps its register allocation
+template <int R, bool HAS_Z, class C, bool EPI, bool HALO>
 __global__ void __launch_bounds__(C::NT, C::CTAS)
-fused3d_kernel(const __grid_constant__ FusedParams p, const __grid_constant__ CUtensorMap tmap)
+fused3d_kernel(const __grid_constant__ FusedParams p, const __grid_constant__ CUtensorMap tmap,
+               const __grid_constant__ ptx::HaloMaps hm)
 {
     constexpr int TX = C::TX, NT = C::NT, CGW = TX / 4, RY = C::RY;
     constexpr int HL = C::HL, PITCH = C::PITCH, NCG = C::NCG, G = C::G, NV = C::NV;
@@ -202,7 +215,7 @@ fused3d_kernel(const __grid_constant__ FusedParams p, const __grid_constant__ CU
 
     // ---- stage one group: one TMA box per plane into raw slot (g & 1), issued by a single thread
     int* iinfo = reinterpret_cast<int*>(rfull + 4) + 8;    // the issuing thread's coordinates, kept out of registers
-    if (tid == 0) { iinfo[0] = x0 - HL; iinfo[1] = y0 - R; iinfo[2] = p_first; iinfo[3] = n_planes; }
+    if (tid == 0) { iinfo[0] = x0 - HL; iinfo[1] = y0 - R; iinfo[2] = p_first; iinfo[3] = n_planes; if (HALO) halo_wait_ready(hm); }
     auto issue = [&](int g) {                               // thread 0 only
         const int cx = iinfo[0], cy = iinfo[1], first = iinfo[2];
         const int planes = min(G, iinfo[3] - g * G);
@@ -210,6 +223,16 @@ fused3d_kernel(const __grid_constant__ FusedParams p, const __grid_constant__ CU
         mbar_expect_tx(bar, (uint32_t)planes * (uint32_t)(p.box_rows * PITCH * sizeof(float)));
         for (int q = 0; q < planes; ++q) {
             int pz = first + g * G + q;
+            if (HALO) {
+                // planes beyond the slab's ends: the neighbours' slabs, read in place over NVLink (their ready
+                // flags were awaited once, before the plane loop)
+                const CUtensorMap* map = &tmap;
+                if (pz < 0 && hm.planes_lo) { map = &hm.lo; pz += hm.planes_lo; }
+                else if (pz >= p.nz_in && hm.planes_hi) { map = &hm.hi; pz -= p.nz_in; }
+                else if (p.mode_z != SEPFILT_CONSTANT) pz = remap_index32(p.mode_z, pz, p.nz_in);
+                tma_load_plane(raw + ((g & 1) * G + q) * RSLOT, map, cx, cy, pz, bar);
+                continue;
+            }
             if (p.mode_z != SEPFILT_CONSTANT) pz = remap_index32(p.mode_z, pz, p.nz_in);   // constant: OOB box -> zeros
             tma_load_plane(raw + ((g & 1) * G + q) * RSLOT, &tmap, cx, cy, pz, bar);
         }
@@ -562,16 +585,25 @@ EncodeTiledFn encode_tiled()
     return fn;
 }
 
-template <int R, bool HAS_Z, class C, bool EPI>
+template <int R, bool HAS_Z, class C, bool EPI, bool HALO = false>
 cudaError_t launch_e(FusedParams& p, cudaStream_t s);
+
+// neighbour halos of the call in flight on this thread (set by launch_fused3d around its launches)
+thread_local const sepfilt_halo* t_halo = nullptr;
 
 template <int R, bool HAS_Z, class C>
 cudaError_t launch_c(FusedParams& p, cudaStream_t s)
 {
+    if (t_halo) {
+        if constexpr (HAS_Z) {
+            if (!p.epilogue) return launch_e<R, HAS_Z, C, false, true>(p, s);
+        }
+        return cudaErrorInvalidValue;       // fused3d_supported admits halos only for plain filters with a z pass
+    }
     return p.epilogue ? launch_e<R, HAS_Z, C, true>(p, s) : launch_e<R, HAS_Z, C, false>(p, s);
 }
 
-template <int R, bool HAS_Z, class C, bool EPI>
+template <int R, bool HAS_Z, class C, bool EPI, bool HALO>
 cudaError_t launch_e(FusedParams& p, cudaStream_t s)
 {
     p.box_rows = p.ty + 2 * R;
@@ -586,11 +618,36 @@ cudaError_t launch_e(FusedParams& p, cudaStream_t s)
             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
         return cudaErrorInvalidValue;
-    auto kern = fused3d_kernel<R, HAS_Z, C, EPI>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
-    if (e != cudaSuccess) return e;
+    ptx::HaloMaps hm;
+    memset(&hm, 0, sizeof hm);
+    if (HALO && t_halo) {
+        const sepfilt_halo& h = *t_halo;
+        const void* src[2] = {h.lo, h.hi};
+        const int planes[2] = {h.lo ? h.planes_lo : 0, h.hi ? h.planes_hi : 0};
+        CUtensorMap* maps[2] = {&hm.lo, &hm.hi};
+        for (int i = 0; i < 2; ++i) {
+            if (!planes[i]) continue;
+            const cuuint64_t hdim[3] = {(cuuint64_t)p.nx, (cuuint64_t)p.ny, (cuuint64_t)planes[i]};
+            if (enc(maps[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(src[i]), hdim, gstride, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+                return cudaErrorInvalidValue;
+        }
+        hm.planes_lo = planes[0]; hm.planes_hi = planes[1];
+        hm.ready_lo = h.ready_lo; hm.ready_hi = h.ready_hi; hm.epoch = h.epoch;
+    }
+    auto kern = fused3d_kernel<R, HAS_Z, C, EPI, HALO>;
+    // the attribute is per (function, device): set once per device, not on every call
+    static bool attr_done[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !attr_done[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+        if (e != cudaSuccess) return e;
+        if (dev >= 0 && dev < 64) attr_done[dev] = true;
+    }
     const long long blocks = (long long)p.tiles_x * p.tiles_y * p.nzseg;
-    kern<<<(unsigned)blocks, C::NT, C::SMEM, s>>>(p, tmap);
+    kern<<<(unsigned)blocks, C::NT, C::SMEM, s>>>(p, tmap, hm);
     return cudaGetLastError();
 }
 
@@ -619,6 +676,15 @@ bool fused3d_supported(const FusedVolume& v, const F32Taps taps[3], bool gradmag
         if (v.mode[a] == SEPFILT_WRAP && taps[a].radius > 0) return false;
     const long long tiles = (long long)((v.nx + 63) / 64) * v.ny;
     if (tiles * v.nz_out > 2147483647LL) return false;
+    if (v.halo) {
+        // neighbour planes come through their own tensor maps: whole slab, a z pass, sources of every
+        // x / y halo cell inside the tile, one launch (the accumulating gradient-magnitude launches are not
+        // instantiated with halos: fused_ws serves that call)
+        if (!has_z || gradmag || v.z_offset != 0 || v.nz_in != v.nz_out || v.ny < 32 || v.nx < 32) return false;
+        if ((v.halo->lo && v.halo->planes_lo < taps[0].radius) || (v.halo->hi && v.halo->planes_hi < taps[0].radius))
+            return false;
+        if (v.nz_in < taps[0].radius) return false;
+    }
     return true;
 }
 
@@ -645,7 +711,8 @@ double plan_tiles(const FusedVolume& v, int R, bool has_z, int tx, int slots, Fu
             if (!has_z) break;
         }
     }
-    if (const char* fty = getenv("SEPFILT_FUSED_TY")) {          // tuning aid: force the tile height
+    static const char* fty = getenv("SEPFILT_FUSED_TY");         // tuning aid (read once): force the tile height
+    if (fty) {
         const int t = atoi(fty);
         if (t >= 1 && t <= TYM) { best_ty = t; best_seg = 1; }
     }
@@ -665,15 +732,7 @@ double plan_tiles(const FusedVolume& v, int R, bool has_z, int tx, int slots, Fu
 template <int R, bool HAS_Z>
 cudaError_t launch_r(const FusedVolume& v, FusedParams& p, cudaStream_t s)
 {
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    // SMs to leave free for a concurrent communication kernel (the sharded path sets this): a
-    // one-wave grid that needs EVERY SM would otherwise serialise behind the SMs NCCL occupies
-    if (const char* rs = getenv("SEPFILT_RESERVE_SMS")) {
-        const int r = atoi(rs);
-        if (r > 0 && r < sms) sms -= r;
-    }
+    const int sms = cached_sm_count();
     {
     using Wide = Cfg<R, 128, 4, 1>;      // 512 threads, one CTA per SM
     using Narrow = Cfg<R, 64, 3, 2>;     // 256 threads, two CTAs per SM: one CTA's barrier waits hide behind the other
@@ -700,9 +759,7 @@ cudaError_t launch_r(const FusedVolume& v, FusedParams& p, cudaStream_t s)
 template <int R>
 cudaError_t launch_wide_xy(const FusedVolume& v, FusedParams& p, cudaStream_t s)
 {
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int sms = cached_sm_count();
     plan_tiles(v, R, false, 128, sms, &p);
     return launch_e<R, false, Cfg<R, 128, 2, 1>, false>(p, s);
 }
@@ -748,6 +805,10 @@ static cudaError_t launch_one(const FusedVolume& v, const F32Taps taps[3], int e
 cudaError_t launch_fused3d(const FusedVolume& v, const F32Taps taps[3], const F32Taps dtaps[3], bool gradmag,
                            cudaStream_t s)
 {
+    struct HaloScope {
+        explicit HaloScope(const sepfilt_halo* h) { t_halo = h; }
+        ~HaloScope() { t_halo = nullptr; }
+    } scope(v.halo);
     if (!gradmag) return launch_one(v, taps, 0, s);
     // gradient magnitude: sqrt(sum_a (D_a prod_{b != a} S_b in)^2), one launch per filtered axis
     const int first = (v.nz_in == 1 && v.nz_out == 1 && taps[0].radius == 0 && dtaps[0].radius == 0) ? 1 : 0;

@@ -109,7 +109,8 @@ template <bool SWZ, int ODD_OFF> __device__ __forceinline__ int ycol_offset(int 
 
 template <class C>
 __global__ void __launch_bounds__(C::NT, 1)
-fws_kernel(const __grid_constant__ WsParams p, const __grid_constant__ CUtensorMap tmap)
+fws_kernel(const __grid_constant__ WsParams p, const __grid_constant__ CUtensorMap tmap,
+           const __grid_constant__ HaloMaps hm)
 {
     constexpr int R = C::R, CPT = C::CPT, TYC = C::TYC, TX = C::TX, TPR = C::TPR;
     constexpr int HL = C::HL, PW = C::PW, NCG = C::NCG, NR = C::NR, NY = C::NY, NF = C::NF, NZF = C::NZF;
@@ -172,10 +173,20 @@ fws_kernel(const __grid_constant__ WsParams p, const __grid_constant__ CUtensorM
         reg_dealloc<C::YREGS>();
         auto issue = [&](int pl) {                               // one lane
             int pz = p_first + pl;
-            if (p.mode_z != SEPFILT_CONSTANT) pz = remap_index32(p.mode_z, pz, p.nz_in);   // constant: OOB box -> zeros
+            const CUtensorMap* map = &tmap;
+            if (pz < 0 && hm.planes_lo) {
+                // a plane of the lower neighbour's slab, read in place over NVLink once its array is ready
+                if (hm.ready_lo) { wait_flag_geq(hm.ready_lo, hm.epoch); fence_proxy_async_all(); }
+                map = &hm.lo; pz += hm.planes_lo;
+            } else if (pz >= p.nz_in && hm.planes_hi) {
+                if (hm.ready_hi) { wait_flag_geq(hm.ready_hi, hm.epoch); fence_proxy_async_all(); }
+                map = &hm.hi; pz -= p.nz_in;
+            } else if (p.mode_z != SEPFILT_CONSTANT) {
+                pz = remap_index32(p.mode_z, pz, p.nz_in);   // constant: OOB box -> zeros
+            }
             uint64_t* bar = &full_raw[pl % NR];
             mbar_expect_tx(bar, BOX_BYTES);
-            tma_load_3d(raw + (pl % NR) * RSLOT, &tmap, x0 - HL, y0 - R, pz, bar);
+            tma_load_3d(raw + (pl % NR) * RSLOT, map, x0 - HL, y0 - R, pz, bar);
         };
         if (tid == 0)
             for (int pl = 0; pl < NR && pl < n_planes; ++pl) issue(pl);
@@ -491,19 +502,7 @@ WsPlan plan_tiles(const FusedVolume& v, int R, bool has_z, int tyc, int sms)
     return best;
 }
 
-int device_sms()
-{
-    static int cached[64] = {0};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev < 0 || dev >= 64) return 148;
-    if (!cached[dev]) {
-        int sms = 148;
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        cached[dev] = sms;
-    }
-    return cached[dev];
-}
+int device_sms() { return cached_sm_count(); }
 
 template <class C>
 cudaError_t launch_cfg(const FusedVolume& v, WsParams& p, const WsPlan& plan, cudaStream_t s)
@@ -522,8 +521,24 @@ cudaError_t launch_cfg(const FusedVolume& v, WsParams& p, const WsPlan& plan, cu
         if (e != cudaSuccess) return e;
         if (dev >= 0 && dev < 64) done[dev] = true;
     }
+    HaloMaps hm;
+    std::memset(&hm, 0, sizeof hm);
+    if (v.halo) {
+        const sepfilt_halo& h = *v.halo;
+        if (h.lo && h.planes_lo) {
+            if (!encode_volume_map(&hm.lo, static_cast<const float*>(h.lo), v.nx, v.ny, h.planes_lo, C::PW, C::BOX_ROWS))
+                return cudaErrorInvalidValue;
+            hm.planes_lo = h.planes_lo;
+        }
+        if (h.hi && h.planes_hi) {
+            if (!encode_volume_map(&hm.hi, static_cast<const float*>(h.hi), v.nx, v.ny, h.planes_hi, C::PW, C::BOX_ROWS))
+                return cudaErrorInvalidValue;
+            hm.planes_hi = h.planes_hi;
+        }
+        hm.ready_lo = h.ready_lo; hm.ready_hi = h.ready_hi; hm.epoch = h.epoch;
+    }
     const long long blocks = (long long)p.tiles_x * p.tiles_y * p.nzseg;
-    kern<<<(unsigned)blocks, C::NT, C::SMEM, s>>>(p, tmap);
+    kern<<<(unsigned)blocks, C::NT, C::SMEM, s>>>(p, tmap, hm);
     return cudaGetLastError();
 }
 
@@ -579,6 +594,10 @@ bool fused_ws_supported(const FusedVolume& v, const F32Taps taps[3], const F32Ta
         if (v.mode[a] == SEPFILT_WRAP && taps[a].radius > 0) return false;
     const long long tiles = (long long)((v.nx + 127) / 128) * ((v.ny + 13) / 14);
     if (tiles * 64 > 2147483647LL) return false;
+    if (v.halo) {
+        if (!has_z || v.z_offset != 0 || v.nz_in != v.nz_out || v.nz_in < r) return false;
+        if ((v.halo->lo && v.halo->planes_lo < r) || (v.halo->hi && v.halo->planes_hi < r)) return false;
+    }
     return true;
 }
 

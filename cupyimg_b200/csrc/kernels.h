@@ -100,6 +100,7 @@ struct FusedVolume {
     int32_t      z_offset;                // out plane z <-> in plane z + z_offset
     int32_t      mode[3];                 // per axis (z, y, x)
     float        cval;
+    const sepfilt_halo* halo;             // neighbour planes beyond the slab's ends (multi-GPU), or nullptr
 };
 bool        fused3d_supported(const FusedVolume& v, const F32Taps taps[3], bool gradmag);
 cudaError_t launch_fused3d(const FusedVolume& v, const F32Taps taps[3], const F32Taps dtaps[3],

@@ -91,7 +91,55 @@ template <int N> __device__ __forceinline__ void reg_alloc()
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
 }
 
+// wait until a flag in global memory (written by a neighbour GPU's stream memory operation) reaches
+// `epoch`; one thread.  5 s without progress traps instead of hanging the device.
+__device__ __forceinline__ void wait_flag_geq(const uint32_t* flag, uint32_t epoch)
+{
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+    if ((int32_t)(v - epoch) >= 0) return;
+    unsigned long long t0, t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (;;) {
+        __nanosleep(200);
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+        if ((int32_t)(v - epoch) >= 0) break;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        if (t1 - t0 > 5000000000ull) __trap();
+    }
+}
+// order the flag read (generic proxy) before the TMA reads (async proxy) of the memory it guards
+__device__ __forceinline__ void fence_proxy_async_all()
+{
+    asm volatile("fence.proxy.async;" ::: "memory");
+}
+
+// tensor maps and flags of the neighbour planes beyond a z-slab's ends (sepfilt_halo, include/sepfilt.h)
+struct HaloMaps {
+    CUtensorMap lo, hi;
+    const uint32_t* ready_lo;
+    const uint32_t* ready_hi;
+    uint32_t epoch;
+    int planes_lo, planes_hi;
+    int pad_;
+};
+
 }  // namespace ptx
+
+// SM count of the current device, looked up once per device (not on every launch)
+inline int cached_sm_count()
+{
+    static int cached[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) return 148;
+    if (!cached[dev]) {
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cached[dev] = sms;
+    }
+    return cached[dev];
+}
 
 // ---- host: cuTensorMapEncodeTiled through the runtime's driver entry point (no link against libcuda)
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,

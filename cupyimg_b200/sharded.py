@@ -6,20 +6,30 @@
   pairs on a side stream, launches the interior planes (which need no halo) on the compute
   stream at once, and launches the two r-plane boundary strips when the halos have landed,
   so the exchange hides behind the interior compute.  Output stays sharded.
+* Float32 volumes whose whole filter runs in one fused launch take the peer-memory path instead
+  (``backend="p2p"``, the default where it applies): the slab lives in symmetric memory
+  (``torch.distributed._symmetric_memory``: CUDA VMM allocations mapped into every rank of the node), and the
+  fused kernel loads the r neighbour planes it needs with TMA straight from the neighbour's slab over
+  NVLink.  No halo buffer, no copy and no communication kernel: the one-wave grid keeps every SM.
+  Readiness travels as 32-bit flags written by stream memory operations (``sepfilt_stream_write32``):
+  "my slab is complete" before the launch, "I have read your planes" after it.
 * Batched 2-D stacks (filtered axes never split) shard over the batch axis with no
   communication: :func:`batch_range`.
 
 The reference is single-GPU (no collectives anywhere); this is the
 B200 scale-out of its per-axis loops (filters.py:651-662, :777-789).
 """
-import os
+import ctypes
 
 import numpy as np
 import torch
 import torch.distributed as dist
 
-from . import _array
+from . import _array, _ffi
 from .scipy.ndimage import filters as _filters
+
+# flag slots of the peer-memory protocol (32-bit words in each rank's symmetric flag array)
+_LO_READY, _HI_READY, _LO_DONE, _HI_DONE = 0, 1, 2, 3
 
 
 def batch_range(n_items, world_size, rank):
@@ -42,7 +52,7 @@ class ZSlabFilter:
     """
 
     def __init__(self, slab_shape, radius, mode="reflect", device=None, dtype=torch.float32, group=None,
-                 cval=0.0):
+                 cval=0.0, backend="auto"):
         self.group = group
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -66,10 +76,115 @@ class ZSlabFilter:
         self.hi_ext = torch.empty(shape, dtype=dtype, device=self.device) if self.has_hi and r else None
         self.on_cuda = self.device.type == "cuda"
         self.comm_stream = torch.cuda.Stream(self.device) if self.on_cuda else None
-        if self.world > 1 and self.on_cuda:
-            # the interior launch overlaps the NCCL send/recv kernels: leave them a few SMs, otherwise a
-            # grid sized to fill every SM in one wave waits for the SMs NCCL holds and runs two waves
-            os.environ.setdefault("SEPFILT_RESERVE_SMS", "8")
+        # ---- peer-memory backend: slab + flags in symmetric memory ----
+        if backend not in ("auto", "p2p", "nccl"):
+            raise ValueError("backend must be 'auto', 'p2p' or 'nccl'")
+        self.slab = None
+        self.epoch = 0
+        self.p2p = False
+        if backend != "nccl" and self.world > 1 and self.on_cuda and dtype == torch.float32 and r > 0:
+            try:
+                self._init_p2p()
+                self.p2p = True
+            except Exception:
+                if backend == "p2p":
+                    raise
+        elif backend == "p2p" and self.world > 1:
+            raise ValueError("the peer-memory backend needs CUDA float32 slabs and a z radius > 0")
+
+    # -- peer-memory backend ---------------------------------------------------------
+    def _init_p2p(self):
+        import torch.distributed._symmetric_memory as symm
+        group = self.group if self.group is not None else dist.group.WORLD
+        self.slab = symm.empty((self.nz, self.ny, self.nx), dtype=torch.float32, device=self.device)
+        self._flags = symm.empty(16, dtype=torch.int32, device=self.device)
+        self._slab_hdl = symm.rendezvous(self.slab, group)
+        self._flags_hdl = symm.rendezvous(self._flags, group)
+        self._flags.zero_()
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group)                       # every rank's flags are zero before anyone writes one
+        self._slab_ptrs = [int(p) for p in self._slab_hdl.buffer_ptrs]
+        self._flag_ptrs = [int(p) for p in self._flags_hdl.buffer_ptrs]
+        self._plane_bytes = self.ny * self.nx * 4
+
+    def _write_flag(self, rank, slot, value, stream):
+        _ffi.check(_ffi.lib().sepfilt_stream_write32(stream, self._flag_ptrs[rank] + 4 * slot, value))
+
+    def begin_fill(self):
+        """Hold the current stream until both neighbours have finished reading this rank's slab in the
+        previous step.  Call before overwriting ``self.slab`` (``run`` does when it copies the input in)."""
+        if not self.p2p or self.epoch == 0:
+            return
+        stream = _array.current_stream(self.device)
+        mine = self._flag_ptrs[self.rank]
+        if self.has_lo:
+            _ffi.check(_ffi.lib().sepfilt_stream_wait32_geq(stream, mine + 4 * _LO_DONE, self.epoch))
+        if self.has_hi:
+            _ffi.check(_ffi.lib().sepfilt_stream_wait32_geq(stream, mine + 4 * _HI_DONE, self.epoch))
+
+    def _run_p2p(self, x, output, specs, dspecs, cval):
+        """One fused launch over the whole slab; the r planes beyond each end are read from the neighbours'
+        slabs.  Returns False (nothing enqueued) when the library has no fused kernel for the request."""
+        inp, out = _array.ingest(self.slab), _array.ingest(output)
+        if not _filters._fused_candidate(inp, out, specs, False, gradmag=dspecs is not None):
+            return False
+        structs = [s.struct() for s in specs]
+        arr = (_ffi.Pass * len(structs))(*[s[0] for s in structs])
+        darr = None
+        if dspecs is not None:
+            dstructs = [s.struct() for s in dspecs]
+            darr = (_ffi.Pass * len(dstructs))(*[s[0] for s in dstructs])
+        L = _ffi.lib()
+        if not L.sepfilt_separable_f32_supported(inp.tensor(), out.tensor(), arr, len(structs),
+                                                 1 if dspecs is not None else 0, float(cval)):
+            return False
+        if x.data_ptr() != self.slab.data_ptr():
+            self.begin_fill()
+            self.slab.copy_(x, non_blocking=True)
+        stream = _array.current_stream(self.device)
+        lower, upper = self._peer(-1), self._peer(+1)
+        epoch = self.epoch + 1
+        r = self.r
+        halo = _ffi.Halo()
+        mine = self._flag_ptrs[self.rank]
+        if self.has_lo:
+            halo.lo = self._slab_ptrs[lower] + (self.nz - r) * self._plane_bytes
+            halo.planes_lo = r
+            halo.ready_lo = mine + 4 * _LO_READY
+        if self.has_hi:
+            halo.hi = self._slab_ptrs[upper]
+            halo.planes_hi = r
+            halo.ready_hi = mine + 4 * _HI_READY
+        halo.epoch = epoch
+        # my slab is complete at this point of the stream: tell the ranks that read it
+        if self.has_lo:
+            self._write_flag(lower, _HI_READY, epoch, stream)      # I am the lower rank's upper neighbour
+        if self.has_hi:
+            self._write_flag(upper, _LO_READY, epoch, stream)
+        rc = L.sepfilt_separable_f32_halo(inp.tensor(), out.tensor(), arr, len(structs), darr,
+                                          1 if dspecs is not None else 0, ctypes.byref(halo), float(cval), stream)
+        self.epoch = epoch
+        ok = rc != _ffi.ERR_UNSUPPORTED
+        if ok:
+            _ffi.check(rc)
+            _ffi.count_launch(1)
+        # the neighbours' planes have been read once the kernel is done (an unsupported request read nothing)
+        if self.has_lo:
+            self._write_flag(lower, _HI_DONE, epoch, stream)
+        if self.has_hi:
+            self._write_flag(upper, _LO_DONE, epoch, stream)
+        return ok
+
+    def _try_p2p(self, x, output, specs, dspecs, dtype_mode):
+        if not self.p2p or dtype_mode == "ndimage" or self.world == 1:
+            return False
+        if tuple(x.shape) != (self.nz, self.ny, self.nx) or tuple(output.shape) != tuple(x.shape):
+            raise _array.OutputShapeError("slab shape does not match the plan")
+        if x.dtype != torch.float32 or output.dtype != torch.float32:
+            return False
+        if not any(s.axis == 0 for s in specs):
+            return False                          # no z pass: nothing to exchange, the plain call serves it
+        return self._run_p2p(x, output, specs, dspecs, self.cval)
 
     # -- halo exchange ---------------------------------------------------------------
     def _peer(self, step):
@@ -144,6 +259,8 @@ class ZSlabFilter:
         if compute is None:
             specs = _filters._gaussian_specs(_array.ingest(x), sigma, order, self.mode, truncate)
             self._check_radius(specs)
+            if self._try_p2p(x, output, specs, None, dtype_mode):
+                return output
             compute = _cuda_compute(specs, self.cval, dtype_mode)
         return self.run(x, output, compute)
 
@@ -153,6 +270,8 @@ class ZSlabFilter:
             output = torch.empty_like(x)
         if compute is None:
             self._check_radius(specs)
+            if self._try_p2p(x, output, list(specs), None, dtype_mode):
+                return output
             compute = _cuda_compute(list(specs), self.cval, dtype_mode)
         return self.run(x, output, compute)
 
@@ -180,6 +299,8 @@ class ZSlabFilter:
                 raise ValueError("sharded gradient magnitude needs sigma > 0 on every axis")
             self._check_radius(deriv)
             cval = self.cval
+            if self._try_p2p(x, output, smooth, deriv, dtype_mode):
+                return output
 
             def compute(src, dst, in_offset0):
                 _filters._gradient_magnitude_window(_array.ingest(src), _array.ingest(dst), smooth, deriv,
@@ -198,5 +319,7 @@ class ZSlabFilter:
                                         uniform=True, size=int(s))
                      for a, (s, o, m) in enumerate(zip(sizes, origins, modes)) if s > 1]
             self._check_radius(specs)
+            if self._try_p2p(x, output, specs, None, dtype_mode):
+                return output
             compute = _cuda_compute(specs, self.cval, dtype_mode)
         return self.run(x, output, compute)

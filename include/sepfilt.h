@@ -148,6 +148,45 @@ SEPFILT_API int sepfilt_separable_f32(const sepfilt_tensor* in, const sepfilt_te
                           const sepfilt_pass* dpasses, int gradient_magnitude,
                           int64_t in_offset0, double cval, void* stream);
 
+/*
+ * z-slab halos read straight from the neighbours' memory (multi-GPU, one process per GPU).
+ * The reference is single-GPU; this is the scale-out of its per-axis loops (filters.py:651-662,
+ * :777-789): the volume is sharded along axis 0 and a rank's z pass needs `radius` planes of RAW
+ * input from each neighbour.  Instead of exchanging them into local buffers first, the fused kernel
+ * loads those planes with TMA directly from the neighbour's array (a peer-mapped pointer: CUDA IPC /
+ * VMM symmetric memory over NVLink), so no copy and no communication kernel sits on the data path.
+ *   lo: the `planes_lo` planes that precede in-plane 0 (the lower neighbour's LAST planes), C-contiguous
+ *       (planes_lo, ny, nx) float32; NULL / 0 planes: the boundary mode applies at the slab's start.
+ *   hi: the `planes_hi` planes that follow the last in-plane (the upper neighbour's FIRST planes).
+ *   ready_lo / ready_hi: 32-bit flags in THIS device's memory; the kernel reads a neighbour's planes only
+ *       after the flag is >= epoch (the neighbour writes it with a stream memory operation once its
+ *       array is complete).  NULL: no wait.  A flag that stays below epoch for 5 s traps the kernel.
+ * planes_lo / planes_hi must be 0 or >= the z radius of the filter.
+ */
+typedef struct {
+    const void*     lo;
+    const void*     hi;
+    int32_t         planes_lo, planes_hi;
+    const uint32_t* ready_lo;
+    const uint32_t* ready_hi;
+    uint32_t        epoch;
+    uint32_t        reserved;
+} sepfilt_halo;
+
+/* sepfilt_separable_f32 on a z-slab with neighbour halos (rank-3 float32, in and out of equal shape,
+ * a z pass present).  SEPFILT_ERR_UNSUPPORTED when no fused kernel takes the request: the caller then
+ * exchanges halos into a local buffer and uses the windowed call. */
+SEPFILT_API int sepfilt_separable_f32_halo(const sepfilt_tensor* in, const sepfilt_tensor* out,
+                               const sepfilt_pass* passes, int npasses,
+                               const sepfilt_pass* dpasses, int gradient_magnitude,
+                               const sepfilt_halo* halo, double cval, void* stream);
+
+/* Stream-ordered 32-bit flag operations (cuStreamWriteValue32 / cuStreamWaitValue32, no kernel, no SM):
+ * write `value` to *addr when the stream reaches this point (addr may be peer-mapped), or hold the
+ * stream until *addr >= value.  These carry the ready / done flags of the halo protocol above. */
+SEPFILT_API int sepfilt_stream_write32(void* stream, void* addr, uint32_t value);
+SEPFILT_API int sepfilt_stream_wait32_geq(void* stream, void* addr, uint32_t value);
+
 /* Kernels enqueued by the calling thread's last successful sepfilt_separable_f32 call (1, or one per
  * axis when the gradient magnitude runs as accumulating launches): lets the host layer report
  * launch counts instead of assuming them. */
