@@ -64,6 +64,9 @@ class Halo(ctypes.Structure):
         ("planes_hi", ctypes.c_int32),
         ("ready_lo", ctypes.c_void_p),
         ("ready_hi", ctypes.c_void_p),
+        ("done_lo", ctypes.c_void_p),
+        ("done_hi", ctypes.c_void_p),
+        ("cta_counter", ctypes.c_void_p),
         ("epoch", ctypes.c_uint32),
         ("reserved", ctypes.c_uint32),
     ]
@@ -72,7 +75,7 @@ class Halo(ctypes.Structure):
 EXPORTS = (
     "sepfilt_version", "sepfilt_last_error", "sepfilt_correlate1d", "sepfilt_separable_f32",
     "sepfilt_separable_f32_supported", "sepfilt_gradmag_step", "sepfilt_copy_cast", "sepfilt_correlate_nd",
-    "sepfilt_last_launch_count", "sepfilt_separable_f32_halo", "sepfilt_stream_write32", "sepfilt_stream_wait32_geq",
+    "sepfilt_last_launch_count", "sepfilt_separable_f32_halo", "sepfilt_stream_write32", "sepfilt_stream_write32x2", "sepfilt_stream_wait32_geq",
 )
 
 _lib = None
@@ -114,6 +117,8 @@ def lib():
         L.sepfilt_separable_f32_halo.restype = ci
         L.sepfilt_stream_write32.argtypes = [vp, vp, ctypes.c_uint32]
         L.sepfilt_stream_write32.restype = ci
+        L.sepfilt_stream_write32x2.argtypes = [vp, vp, vp, ctypes.c_uint32]
+        L.sepfilt_stream_write32x2.restype = ci
         L.sepfilt_stream_wait32_geq.argtypes = [vp, vp, ctypes.c_uint32]
         L.sepfilt_stream_wait32_geq.restype = ci
         L.sepfilt_gradmag_step.argtypes = [vp, vp, i64, ci, ci, vp]

@@ -448,6 +448,37 @@ int sepfilt_stream_write32(void* stream, void* addr, uint32_t value)
     return SEPFILT_OK;
 }
 
+int sepfilt_stream_write32x2(void* stream, void* addr_a, void* addr_b, uint32_t value)
+{
+    typedef CUresult (*BatchFn)(CUstream, unsigned int, CUstreamBatchMemOpParams*, unsigned int);
+    static BatchFn fn = [] {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuStreamBatchMemOp", &f, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            f = nullptr;
+        return reinterpret_cast<BatchFn>(f);
+    }();
+    if (!fn) return fail(SEPFILT_ERR_CUDA, "cuStreamBatchMemOp is not available");
+    CUstreamBatchMemOpParams ops[2];
+    memset(ops, 0, sizeof ops);
+    unsigned int n = 0;
+    void* addrs[2] = {addr_a, addr_b};
+    for (void* a : addrs) {
+        if (!a) continue;
+        if (reinterpret_cast<uintptr_t>(a) & 3) return fail(SEPFILT_ERR_INVALID, "flag address must be 4-byte aligned");
+        ops[n].writeValue.operation = CU_STREAM_MEM_OP_WRITE_VALUE_32;
+        ops[n].writeValue.address = reinterpret_cast<CUdeviceptr>(a);
+        ops[n].writeValue.value = value;
+        ops[n].writeValue.flags = CU_STREAM_WRITE_VALUE_DEFAULT;
+        ++n;
+    }
+    if (!n) return SEPFILT_OK;
+    const CUresult r = fn(static_cast<CUstream>(stream), n, ops, 0);
+    if (r != CUDA_SUCCESS) return fail(SEPFILT_ERR_CUDA, "cuStreamBatchMemOp failed (%d)", (int)r);
+    return SEPFILT_OK;
+}
+
 int sepfilt_stream_wait32_geq(void* stream, void* addr, uint32_t value)
 {
     static StreamValue32Fn fn = stream_value_fn("cuStreamWaitValue32");

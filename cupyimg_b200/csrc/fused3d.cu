@@ -536,6 +536,7 @@ fused3d_kernel(const __grid_constant__ FusedParams p, const __grid_constant__ CU
         __syncthreads();
         if (tid == 0 && k + 3 < n_groups) { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); issue(k + 3); }
     }
+    if (HALO && tid == 0) ptx::halo_signal_done(hm, gridDim.x);   // every plane this CTA staged has landed and been read
 #ifdef SEPFILT_DEBUG_CYCLES
     if (tid == 0 && blockIdx.x < 1024) {
         unsigned smid;
@@ -635,6 +636,7 @@ cudaError_t launch_e(FusedParams& p, cudaStream_t s)
         }
         hm.planes_lo = planes[0]; hm.planes_hi = planes[1];
         hm.ready_lo = h.ready_lo; hm.ready_hi = h.ready_hi; hm.epoch = h.epoch;
+        hm.done_lo = h.done_lo; hm.done_hi = h.done_hi; hm.counter = h.cta_counter;
     }
     auto kern = fused3d_kernel<R, HAS_Z, C, EPI, HALO>;
     // the attribute is per (function, device): set once per device, not on every call

@@ -159,7 +159,7 @@ fws_kernel(const __grid_constant__ WsParams p, const __grid_constant__ CUtensorM
             coltab[i] = ycol_offset<SWZ, C::ODD_OFF>(gx - (x0 - HL)) | (ycol_offset<SWZ, C::ODD_OFF>(sx - (x0 - HL)) << 16);
         }
         if (lane == 0) {
-            meta[0] = 0;
+            meta[0] = 0; meta[1] = 0;
             for (int i = 0; i < NR; ++i) mbar_init(&full_raw[i], 1);
             for (int i = 0; i < NY; ++i) { mbar_init(&full_y[i], 1); mbar_init(&empty_y[i], C::NXZW); }
             mbar_fence_init();
@@ -302,6 +302,9 @@ fws_kernel(const __grid_constant__ WsParams p, const __grid_constant__ CUtensorM
             }
             if (lane == 0) mbar_arrive(&full_y[ys]);
         }
+        // the last Y warp of the CTA to run out of planes: every staged plane has landed and been filtered
+        if (lane == 0 && (hm.planes_lo | hm.planes_hi) && atomicAdd(&meta[1], 1) == C::NYW - 1)
+            halo_signal_done(hm, gridDim.x);
         return;
     }
 
@@ -536,6 +539,7 @@ cudaError_t launch_cfg(const FusedVolume& v, WsParams& p, const WsPlan& plan, cu
             hm.planes_hi = h.planes_hi;
         }
         hm.ready_lo = h.ready_lo; hm.ready_hi = h.ready_hi; hm.epoch = h.epoch;
+        hm.done_lo = h.done_lo; hm.done_hi = h.done_hi; hm.counter = h.cta_counter;
     }
     const long long blocks = (long long)p.tiles_x * p.tiles_y * p.nzseg;
     kern<<<(unsigned)blocks, C::NT, C::SMEM, s>>>(p, tmap, hm);

@@ -119,10 +119,26 @@ struct HaloMaps {
     CUtensorMap lo, hi;
     const uint32_t* ready_lo;
     const uint32_t* ready_hi;
+    uint32_t* done_lo;
+    uint32_t* done_hi;
+    unsigned int* counter;
     uint32_t epoch;
     int planes_lo, planes_hi;
     int pad_;
 };
+
+// one thread per CTA, after the CTA's last read of neighbour planes: the last CTA of the grid tells the
+// neighbours (flags in THEIR memory) that their planes have been read, and re-arms the counter
+static __device__ __noinline__ void halo_signal_done(const HaloMaps& hm, unsigned int n_ctas)
+{
+    if (!hm.counter) return;
+    __threadfence();
+    if (atomicAdd(hm.counter, 1u) != n_ctas - 1) return;
+    *hm.counter = 0;
+    __threadfence_system();
+    if (hm.done_lo) asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(hm.done_lo), "r"(hm.epoch) : "memory");
+    if (hm.done_hi) asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(hm.done_hi), "r"(hm.epoch) : "memory");
+}
 
 }  // namespace ptx
 

@@ -29,7 +29,7 @@ from . import _array, _ffi
 from .scipy.ndimage import filters as _filters
 
 # flag slots of the peer-memory protocol (32-bit words in each rank's symmetric flag array)
-_LO_READY, _HI_READY, _LO_DONE, _HI_DONE = 0, 1, 2, 3
+_LO_READY, _HI_READY, _LO_DONE, _HI_DONE, _CTA_COUNTER = 0, 1, 2, 3, 8
 
 
 def batch_range(n_items, world_size, rank):
@@ -76,6 +76,7 @@ class ZSlabFilter:
         self.hi_ext = torch.empty(shape, dtype=dtype, device=self.device) if self.has_hi and r else None
         self.on_cuda = self.device.type == "cuda"
         self.comm_stream = torch.cuda.Stream(self.device) if self.on_cuda else None
+        self.comm_stream2 = torch.cuda.Stream(self.device) if self.on_cuda else None
         # ---- peer-memory backend: slab + flags in symmetric memory ----
         if backend not in ("auto", "p2p", "nccl"):
             raise ValueError("backend must be 'auto', 'p2p' or 'nccl'")
@@ -106,6 +107,17 @@ class ZSlabFilter:
         self._slab_ptrs = [int(p) for p in self._slab_hdl.buffer_ptrs]
         self._flag_ptrs = [int(p) for p in self._flags_hdl.buffer_ptrs]
         self._plane_bytes = self.ny * self.nx * 4
+        # "pull": the copy engines fetch the neighbours' r planes into local pads first, each plane
+        # crossing NVLink once; "direct": the kernel's TMA boxes read them in place (every tile re-reads its
+        # x / y halo over NVLink, which the local L2 does not cache: measured slower on 512^2 planes)
+        self.p2p_mode = "auto"
+        r = self.r
+        shape = (self.nz, self.ny, self.nx)
+        lower, upper = self._peer(-1), self._peer(+1)
+        self._peer_lo = self._slab_hdl.get_buffer(lower, shape, torch.float32)[self.nz - r:] if self.has_lo else None
+        self._peer_hi = self._slab_hdl.get_buffer(upper, shape, torch.float32)[:r] if self.has_hi else None
+        self._pad_lo = torch.empty((r, self.ny, self.nx), dtype=torch.float32, device=self.device) if self.has_lo else None
+        self._pad_hi = torch.empty((r, self.ny, self.nx), dtype=torch.float32, device=self.device) if self.has_hi else None
 
     def _write_flag(self, rank, slot, value, stream):
         _ffi.check(_ffi.lib().sepfilt_stream_write32(stream, self._flag_ptrs[rank] + 4 * slot, value))
@@ -147,20 +159,44 @@ class ZSlabFilter:
         r = self.r
         halo = _ffi.Halo()
         mine = self._flag_ptrs[self.rank]
+        # the warp-specialised kernel (gradient magnitude) waits for a neighbour's flag only when its march reaches
+        # that neighbour's planes and spreads the reads over its z segments: in place is faster there
+        mode = self.p2p_mode if self.p2p_mode != "auto" else ("direct" if dspecs is not None else "pull")
+        pull = mode == "pull"
         if self.has_lo:
-            halo.lo = self._slab_ptrs[lower] + (self.nz - r) * self._plane_bytes
+            halo.lo = self._pad_lo.data_ptr() if pull else self._slab_ptrs[lower] + (self.nz - r) * self._plane_bytes
             halo.planes_lo = r
-            halo.ready_lo = mine + 4 * _LO_READY
+            halo.ready_lo = None if pull else mine + 4 * _LO_READY
         if self.has_hi:
-            halo.hi = self._slab_ptrs[upper]
+            halo.hi = self._pad_hi.data_ptr() if pull else self._slab_ptrs[upper]
             halo.planes_hi = r
-            halo.ready_hi = mine + 4 * _HI_READY
+            halo.ready_hi = None if pull else mine + 4 * _HI_READY
         halo.epoch = epoch
-        # my slab is complete at this point of the stream: tell the ranks that read it
+        # the kernel's last CTA tells the neighbours that their planes have been read (no stream operation
+        # after the launch): I am the lower rank's UPPER neighbour, so I set its HI_DONE flag
+        halo.cta_counter = mine + 4 * _CTA_COUNTER
         if self.has_lo:
-            self._write_flag(lower, _HI_READY, epoch, stream)      # I am the lower rank's upper neighbour
+            halo.done_lo = self._flag_ptrs[lower] + 4 * _HI_DONE
         if self.has_hi:
-            self._write_flag(upper, _LO_READY, epoch, stream)
+            halo.done_hi = self._flag_ptrs[upper] + 4 * _LO_DONE
+        # my slab is complete at this point of the stream: tell the ranks that read it (one batched memop)
+        _ffi.check(L.sepfilt_stream_write32x2(
+            stream, self._flag_ptrs[lower] + 4 * _HI_READY if self.has_lo else None,
+            self._flag_ptrs[upper] + 4 * _LO_READY if self.has_hi else None, epoch))
+        if pull:
+            # side stream: wait (stream memory operation, no SM) until a neighbour's slab is complete, then let a
+            # copy engine pull its r planes over NVLink; the launch waits for both pads
+            main = torch.cuda.current_stream(self.device)
+            sides = ((self.has_lo, self.comm_stream, _LO_READY, self._pad_lo, self._peer_lo),
+                     (self.has_hi, self.comm_stream2, _HI_READY, self._pad_hi, self._peer_hi))
+            for present, side, slot, pad, peer_planes in sides:      # one stream per side: two copy engines at once
+                if not present:
+                    continue
+                side.wait_stream(main)                               # the previous launch has finished reading the pad
+                with torch.cuda.stream(side):
+                    _ffi.check(L.sepfilt_stream_wait32_geq(_array.current_stream(self.device), mine + 4 * slot, epoch))
+                    pad.copy_(peer_planes, non_blocking=True)
+                main.wait_stream(side)
         rc = L.sepfilt_separable_f32_halo(inp.tensor(), out.tensor(), arr, len(structs), darr,
                                           1 if dspecs is not None else 0, ctypes.byref(halo), float(cval), stream)
         self.epoch = epoch
@@ -168,11 +204,12 @@ class ZSlabFilter:
         if ok:
             _ffi.check(rc)
             _ffi.count_launch(1)
-        # the neighbours' planes have been read once the kernel is done (an unsupported request read nothing)
-        if self.has_lo:
-            self._write_flag(lower, _HI_DONE, epoch, stream)
-        if self.has_hi:
-            self._write_flag(upper, _LO_DONE, epoch, stream)
+        if not ok:
+            # nothing was launched: release the neighbours by hand (an unsupported request read nothing)
+            if self.has_lo:
+                self._write_flag(lower, _HI_DONE, epoch, stream)
+            if self.has_hi:
+                self._write_flag(upper, _LO_DONE, epoch, stream)
         return ok
 
     def _try_p2p(self, x, output, specs, dspecs, dtype_mode):

@@ -161,6 +161,10 @@ SEPFILT_API int sepfilt_separable_f32(const sepfilt_tensor* in, const sepfilt_te
  *   ready_lo / ready_hi: 32-bit flags in THIS device's memory; the kernel reads a neighbour's planes only
  *       after the flag is >= epoch (the neighbour writes it with a stream memory operation once its
  *       array is complete).  NULL: no wait.  A flag that stays below epoch for 5 s traps the kernel.
+ *   done_lo / done_hi: 32-bit flags in the NEIGHBOURS' memory (peer-mapped) that the kernel sets to epoch
+ *       when its last CTA has finished — "I have read your planes, you may overwrite them" — so that no
+ *       stream operation is needed after the launch.  NULL: not signalled.  Needs cta_counter: one 32-bit
+ *       word of THIS device's memory, zero before the first launch (the kernel leaves it zero).
  * planes_lo / planes_hi must be 0 or >= the z radius of the filter.
  */
 typedef struct {
@@ -169,6 +173,9 @@ typedef struct {
     int32_t         planes_lo, planes_hi;
     const uint32_t* ready_lo;
     const uint32_t* ready_hi;
+    uint32_t*       done_lo;
+    uint32_t*       done_hi;
+    uint32_t*       cta_counter;
     uint32_t        epoch;
     uint32_t        reserved;
 } sepfilt_halo;
@@ -185,6 +192,8 @@ SEPFILT_API int sepfilt_separable_f32_halo(const sepfilt_tensor* in, const sepfi
  * write `value` to *addr when the stream reaches this point (addr may be peer-mapped), or hold the
  * stream until *addr >= value.  These carry the ready / done flags of the halo protocol above. */
 SEPFILT_API int sepfilt_stream_write32(void* stream, void* addr, uint32_t value);
+/* the same value to two addresses in ONE batched stream operation (either may be NULL) */
+SEPFILT_API int sepfilt_stream_write32x2(void* stream, void* addr_a, void* addr_b, uint32_t value);
 SEPFILT_API int sepfilt_stream_wait32_geq(void* stream, void* addr, uint32_t value);
 
 /* Kernels enqueued by the calling thread's last successful sepfilt_separable_f32 call (1, or one per
