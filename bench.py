@@ -275,20 +275,18 @@ def _time_steps(torch, dist, world, dev, fn, steps, warmup, sampler):
 
 
 def _checksum(torch, dist, world, dev, out):
-    """float64 sum of this rank's output, gathered and added in rank order: identical for every N when the
-    sharded outputs are bit-identical to the single-GPU ones (per-plane sums are added in plane order)."""
+    """float64 checksum of the global result: per-plane sums (one float64 reduction per plane), gathered from all
+    ranks and added on the host in global plane order — the same additions for every N, so the value is
+    identical across rank counts exactly when the sharded outputs are bit-identical to the single-GPU ones."""
     per_plane = out.reshape(out.shape[0], -1).to(torch.float64).sum(dim=1)
-    s = torch.zeros(1, dtype=torch.float64, device=dev)
-    for v in per_plane.cpu().tolist():
-        s += v
     if world > 1:
-        parts = [torch.zeros_like(s) for _ in range(world)]
-        dist.all_gather(parts, s)
-        tot = 0.0
-        for p in parts:
-            tot += float(p.item())
-        return tot
-    return float(s.item())
+        parts = [torch.zeros_like(per_plane) for _ in range(world)]
+        dist.all_gather(parts, per_plane)
+        per_plane = torch.cat(parts)
+    tot = 0.0
+    for v in per_plane.cpu().tolist():
+        tot += v
+    return tot
 
 
 def leg_zsharded(torch, dist, np, rank, world, dev, sampler, name, n, kind, sigma, steps, warmup, tag):
@@ -325,8 +323,7 @@ def leg_zsharded(torch, dist, np, rank, world, dev, sampler, name, n, kind, sigm
     torch.cuda.synchronize()
     res = {"workload": name, "global_volume": [n, n, n], "slab_per_gpu": [nz, n, n], "ms_per_step": ms,
            "value": n ** 3 / ms / 1e6, "unit": UNIT, "launches_per_step_per_gpu": launches, "steps": steps,
-           "scaling": "strong", "halo_backend": ("peer memory (TMA over NVLink)" if plan is not None and plan.p2p else
-                                                 ("nccl send/recv" if world > 1 else "none")),
+           "scaling": "strong", "halo_backend": (plan.last_backend if plan is not None else "none"),
            "algorithmic_GBps_per_gpu": nz * n * n * 8 / ms / 1e6}
     # ---- parity: one brick per rank against the oracle (a corner brick on the first rank) ----
     oracle.THREADS = max(1, min(16, os.cpu_count() or 1))

@@ -167,6 +167,14 @@ def ingest(x, name="input"):
         dev = getattr(getattr(x, "device", None), "id", None)
         if dev is None:
             dev = torch.cuda.current_device()
+        # CAI v3: work the producer queued on its stream must be complete before the array is read.  1 is the
+        # legacy default stream (torch's default stream: already ordered), 2 the per-thread default stream.
+        stream = cai.get("stream")
+        if isinstance(stream, int) and stream > 2:
+            ext = torch.cuda.ExternalStream(stream, device=torch.device("cuda", dev))
+            torch.cuda.current_stream(dev).wait_stream(ext)
+        elif stream == 2:
+            torch.cuda.synchronize(dev)
         foreign = type(x).__module__.split(".")[0]
         return DevArray(cai["data"][0] or 0, shape, strides, dt, dev, x, foreign)
     if hasattr(x, "__dlpack__") and not isinstance(x, np.ndarray):

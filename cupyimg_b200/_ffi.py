@@ -113,7 +113,7 @@ def lib():
         L.sepfilt_separable_f32_supported.argtypes = [TP, TP, PP, ci, ci, dbl]
         L.sepfilt_separable_f32_supported.restype = ci
         L.sepfilt_last_launch_count.restype = ci
-        L.sepfilt_separable_f32_halo.argtypes = [TP, TP, PP, ci, PP, ci, ctypes.POINTER(Halo), dbl, vp]
+        L.sepfilt_separable_f32_halo.argtypes = [TP, TP, PP, ci, PP, ci, ctypes.POINTER(Halo), i64, dbl, vp]
         L.sepfilt_separable_f32_halo.restype = ci
         L.sepfilt_stream_write32.argtypes = [vp, vp, ctypes.c_uint32]
         L.sepfilt_stream_write32.restype = ci

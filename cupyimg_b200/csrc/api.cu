@@ -166,7 +166,8 @@ int sepfilt_correlate1d(const sepfilt_tensor* in, const sepfilt_tensor* out,
         F32Taps taps;
         if (!pass_to_f32_taps(pass, &taps))
             return fail(SEPFILT_ERR_UNSUPPORTED, "filter radius exceeds %d", SEPFILT_FAST_MAX_RADIUS);
-        if (in->shape[axis] > 2147483647LL - 64 || out->shape[axis] > 2147483647LL - 64 ||
+        // the 32-bit boundary fold computes 2n: axes beyond 2^30 elements take the 64-bit exact kernel
+        if (in->shape[axis] > 1073741824LL || out->shape[axis] > 1073741824LL ||
             in_offset > 2147483647LL / 2 || in_offset < -2147483647LL / 2)
             return fail(SEPFILT_ERR_UNSUPPORTED, "axis too long for the tiled pass");
         F32Line g;
@@ -344,7 +345,7 @@ static int build_fused(const sepfilt_tensor* in, const sepfilt_tensor* out,
     v->in = static_cast<const float*>(in->ptr);
     v->out = static_cast<float*>(out->ptr);
     if (nd == 3) {
-        if (in->shape[0] > 2147483647LL || out->shape[0] > 2147483647LL) UNSUP("too many planes");
+        if (in->shape[0] > 1073741824LL || out->shape[0] > 1073741824LL) UNSUP("too many planes");
         v->nz_in = (int32_t)in->shape[0];
         v->nz_out = (int32_t)out->shape[0];
         v->z_offset = (int32_t)in_offset0;
@@ -352,7 +353,7 @@ static int build_fused(const sepfilt_tensor* in, const sepfilt_tensor* out,
         v->nz_in = v->nz_out = 1;
         v->z_offset = 0;
     }
-    if (in->shape[nd - 2] > 2147483647LL || in->shape[nd - 1] > 2147483647LL) UNSUP("plane too large");
+    if (in->shape[nd - 2] > 1073741824LL || in->shape[nd - 1] > 1073741824LL) UNSUP("plane too large");
     v->ny = (int32_t)in->shape[nd - 2];
     v->nx = (int32_t)in->shape[nd - 1];
     v->cval = (float)cval;
@@ -407,12 +408,12 @@ int sepfilt_last_launch_count(void) { return g_last_launches; }
 int sepfilt_separable_f32_halo(const sepfilt_tensor* in, const sepfilt_tensor* out,
                                const sepfilt_pass* passes, int npasses,
                                const sepfilt_pass* dpasses, int gradient_magnitude,
-                               const sepfilt_halo* halo, double cval, void* stream)
+                               const sepfilt_halo* halo, int64_t in_offset0, double cval, void* stream)
 {
     if (!halo) return fail(SEPFILT_ERR_INVALID, "halo descriptor is NULL");
     FusedVolume v;
     F32Taps taps[3], dtaps[3];
-    int rc = build_fused(in, out, passes, npasses, dpasses, gradient_magnitude, 0, cval, &v, taps, dtaps, true, halo);
+    int rc = build_fused(in, out, passes, npasses, dpasses, gradient_magnitude, in_offset0, cval, &v, taps, dtaps, true, halo);
     if (rc != SEPFILT_OK) return rc;
     if (numel(out) == 0) return SEPFILT_OK;
     DeviceGuard guard(in->device);

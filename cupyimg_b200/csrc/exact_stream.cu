@@ -392,12 +392,15 @@ bool exact_stream_supported(const ExactTiledGeom& g, int K, int symmetric)
     const int R = stream_bucket(K / 2);
     if (R < 0) return false;
     if (g.in_dtype != g.out_dtype) return false;
+    // zero padding to the bucket is bit-neutral for finite data only: 0 * NaN / 0 * Inf would poison outputs
+    // beyond the true footprint, so float arrays take this kernel only when the radius IS the bucket
+    if ((g.in_dtype == SEPFILT_F32 || g.in_dtype == SEPFILT_F64) && R != K / 2) return false;
     switch (g.in_dtype) {
     case SEPFILT_U8: case SEPFILT_I16: case SEPFILT_U16: case SEPFILT_F32: case SEPFILT_F64: break;
     default: return false;
     }
     if (g.outer <= 0 || g.inner <= 0 || g.n_in <= 0 || g.n_out <= 0) return false;
-    if (g.n_in > 2147483647LL - 4096 || g.n_out > 2147483647LL - 4096) return false;
+    if (g.n_in > 1073741824LL /* 2n must fit an int in the boundary fold */ || g.n_out > 1073741824LL /* 2n must fit an int in the boundary fold */) return false;
     if (g.shift > 1073741824LL || g.shift < -1073741824LL) return false;
     const int es = dtype_size(g.in_dtype);
     const uintptr_t a = reinterpret_cast<uintptr_t>(g.in) | reinterpret_cast<uintptr_t>(g.out);

@@ -211,8 +211,10 @@ bool exact_tiled_supported(const ExactTiledGeom& g, int K, int symmetric)
 {
     if (!(K & 1) || (symmetric != 1 && symmetric != -1)) return false;
     if (sym_bucket(K / 2) < 0) return false;
+    // zero padding is bit-neutral for finite data only (0 * NaN): float inputs need the radius to be the bucket
+    if ((g.in_dtype == SEPFILT_F32 || g.in_dtype == SEPFILT_F64) && sym_bucket(K / 2) != K / 2) return false;
     if (g.outer <= 0 || g.inner <= 0 || g.n_in <= 0 || g.n_out <= 0) return false;
-    if (g.n_in > 2147483647LL - 4096 || g.n_out > 2147483647LL - 4096) return false;
+    if (g.n_in > 1073741824LL /* 2n must fit an int in the boundary fold */ || g.n_out > 1073741824LL /* 2n must fit an int in the boundary fold */) return false;
     if (g.shift > 1073741824LL || g.shift < -1073741824LL) return false;
     if (g.inner == 1) {
         if ((g.outer + XR_ROWS - 1) / XR_ROWS > 2147483647LL || (g.n_out + XR_W - 1) / XR_W > 65535) return false;

@@ -193,9 +193,8 @@ corr1d_f32_col_kernel(const __grid_constant__ F32Line g, const __grid_constant__
 // =================================== host side ===================================
 static int radius_bucket(int r)
 {
-    static const int buckets[] = {1, 2, 3, 4, 6, 8, 12, 16};
-    for (int b : buckets) if (r <= b) return b;
-    return -1;
+    // one instantiation per radius: no zero padding (0 * NaN would spread non-finite samples, unlike scipy)
+    return (r >= 1 && r <= 16) ? r : -1;
 }
 
 bool f32_line_supported(const F32Line& g, int radius)
@@ -246,9 +245,17 @@ cudaError_t launch_f32_corr1d(const F32Line& g, const F32Taps& t, cudaStream_t s
     case 2: return launch_bucket<2>(g, t, s);
     case 3: return launch_bucket<3>(g, t, s);
     case 4: return launch_bucket<4>(g, t, s);
+    case 5: return launch_bucket<5>(g, t, s);
     case 6: return launch_bucket<6>(g, t, s);
+    case 7: return launch_bucket<7>(g, t, s);
     case 8: return launch_bucket<8>(g, t, s);
+    case 9: return launch_bucket<9>(g, t, s);
+    case 10: return launch_bucket<10>(g, t, s);
+    case 11: return launch_bucket<11>(g, t, s);
     case 12: return launch_bucket<12>(g, t, s);
+    case 13: return launch_bucket<13>(g, t, s);
+    case 14: return launch_bucket<14>(g, t, s);
+    case 15: return launch_bucket<15>(g, t, s);
     case 16: return launch_bucket<16>(g, t, s);
     default: return cudaErrorInvalidValue;
     }

@@ -17,6 +17,7 @@
 // column vector) stay on the shared-memory tiles of f32_1d.cu.
 #include "common.cuh"
 #include "kernels.h"
+#include "ptx.cuh"
 
 namespace sepfilt {
 
@@ -138,6 +139,74 @@ f32_stream_col_kernel(const __grid_constant__ FStreamParams p)
     }
 }
 
+// ---- column kernel for wide filters (radius 9..16): two columns per thread as ONE packed register pair, every
+// update a packed fma.rn.f32x2 with a scalar-broadcast tap.  The scalar version above unrolls to (2R+1)^2 * 2
+// FFMA — 35 KB of code at radius 16, more than the instruction cache holds (measured 0.34-0.67 ms per 512^3
+// pass); packed it is half of that and stays resident.
+template <int R> struct FCol2Geom {
+    static constexpr int W = 2 * R + 1;
+    static constexpr int ring()
+    {
+        int best = 1;
+        for (int p = 1; p <= W; ++p)
+            if (W % p == 0 && p <= 13) best = p;              // largest divisor of W up to 13 rows in flight
+        return best;
+    }
+    static constexpr int P = ring();
+};
+
+template <int R>
+__global__ void __launch_bounds__(128, 3)
+f32_stream_col2_kernel(const __grid_constant__ FStreamParams p)
+{
+    using ptx::u64;
+    typedef FCol2Geom<R> G;
+    constexpr int W = G::W, P = G::P;
+    const int64_t bx = blockIdx.x;
+    const int64_t o = bx / p.xblocks;
+    const int64_t col = ((bx - o * p.xblocks) * 128 + threadIdx.x) * 2;
+    if (col >= p.inner) return;
+    const int p0 = blockIdx.y * p.seg;
+    const int p_end = min(p0 + p.seg, p.n_out);
+    const float* __restrict__ in = p.in + o * (int64_t)p.n_in * p.inner + col;
+    float* __restrict__ out = p.out + o * (int64_t)p.n_out * p.inner + col;
+    const int q0 = p0 + p.shift - R;
+    const int n_steps = (p_end - p0) + 2 * R;
+
+    auto fetch = [&](int q) -> u64 {
+        const int m = fremap_fast(p.mode, q, p.n_in);
+        if (m < 0) return ptx::pack2(p.cval, p.cval);
+        return *reinterpret_cast<const u64*>(in + (int64_t)m * p.inner);
+    };
+    u64 pre[P];
+#pragma unroll
+    for (int i = 0; i < P; ++i) pre[i] = fetch(q0 + i);
+    u64 acc[W];
+#pragma unroll
+    for (int j = 0; j < W; ++j) acc[j] = 0ull;
+
+    for (int base = 0; base < n_steps; base += W) {
+        const bool interior = q0 + base >= 0 && q0 + base + W + P <= p.n_in && base + W <= n_steps;
+#pragma unroll
+        for (int s = 0; s < W; ++s) {
+            const int t = base + s;
+            if (!interior && t >= n_steps) break;
+            const u64 v = pre[s % P];
+            // volatile: the load must be ISSUED here, P rows ahead of its use (ptxas otherwise sinks it next to
+            // the consumer and every step waits for DRAM: 62 % long-scoreboard stalls)
+            if (interior) asm volatile("ld.global.nc.b64 %0, [%1];" : "=l"(pre[s % P]) : "l"(in + (int64_t)(q0 + t + P) * p.inner));
+            else if (t + P < n_steps) pre[s % P] = fetch(q0 + t + P);
+            // logical accumulator j lives in slot (j + s) % W at step s of a block (in place, no moves)
+#pragma unroll
+            for (int j = 0; j < 2 * R; ++j)
+                acc[(j + 1 + s) % W] = ptx::fma2s(v, p.w[2 * R - j], acc[(j + 1 + s) % W]);
+            acc[s % W] = ptx::mul2s(v, p.w[0]);
+            if (t >= 2 * R)
+                *reinterpret_cast<u64*>(out + (int64_t)(p0 + t - 2 * R) * p.inner) = acc[(s + 1) % W];
+        }
+    }
+}
+
 // ---- row kernel ----
 constexpr int FROW_P = 8;            // outputs per thread
 constexpr int FROW_THREADS = 128;
@@ -159,8 +228,8 @@ f32_stream_row_kernel(const __grid_constant__ FStreamParams p)
     // Aligned rows (the common case): the halo of the first / last thread of a row is the mirror image of
     // elements the thread already holds, so it is filled by register selects instead of an element-wise
     // gather (which cost a second round of dependent loads in every warp holding an edge thread).
-    const bool reg_edges = vec_ok && p.shift == 0 && p.n_in == p.n_out && (p.n_in & 7) == 0 && p.n_in >= 16 &&
-                           p.mode != SEPFILT_WRAP && H <= 2;
+    const bool reg_edges = vec_ok && p.shift == 0 && p.n_in == p.n_out && (p.n_in & 7) == 0 && p.n_in >= 8 * H + 8 &&
+                           p.mode != SEPFILT_WRAP;
     float win[4 * NW];
 #pragma unroll
     for (int j = 0; j < NW; ++j) {
@@ -215,14 +284,23 @@ f32_stream_row_kernel(const __grid_constant__ FStreamParams p)
     }
 }
 
+// one instantiation per radius: a tap set is never zero-padded to a wider bucket (0 * NaN / 0 * Inf would
+// spread a non-finite input sample beyond the true footprint of the filter, unlike scipy)
 int fstream_bucket(int r)
 {
-    static const int buckets[] = {1, 2, 3, 4, 6, 8, 12, 16};
-    for (int b : buckets) if (r <= b) return b;
-    return -1;
+    return (r >= 1 && r <= 16) ? r : -1;
 }
 
 int fcols(int R) { return R <= 6 ? 4 : 2; }
+
+template <int R> struct ColKernel {
+    static auto get()
+    {
+        if constexpr (R > 8) return f32_stream_col2_kernel<R>;
+        else return f32_stream_col_kernel<R>;
+    }
+    static constexpr int fallback_ctas() { if constexpr (R > 8) return 3; else return FColGeom<R>::CTAS; }
+};
 
 template <int R>
 cudaError_t launch_fstream(FStreamParams& p, const F32Taps& t, cudaStream_t s)
@@ -236,13 +314,11 @@ cudaError_t launch_fstream(FStreamParams& p, const F32Taps& t, cudaStream_t s)
     }
     static const int per_sm = [] {
         int n = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, f32_stream_col_kernel<R>, 128, 0) != cudaSuccess || n < 1)
-            n = FColGeom<R>::CTAS;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, ColKernel<R>::get(), 128, 0) != cudaSuccess || n < 1)
+            n = ColKernel<R>::fallback_ctas();
         return n;
     }();
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int sms = cached_sm_count();
     // segment length: whole waves of the resident CTA slots, least halo re-reading (2R rows per segment)
     const int64_t slots = (int64_t)sms * per_sm, cols = p.outer * p.xblocks;
     double best = 1e300;
@@ -258,7 +334,7 @@ cudaError_t launch_fstream(FStreamParams& p, const F32Taps& t, cudaStream_t s)
     p.seg = best_seg;
     if ((p.n_out + p.seg - 1) / p.seg > 65535) p.seg = (int32_t)((p.n_out + 65534) / 65535);
     dim3 grid((unsigned)cols, (unsigned)((p.n_out + p.seg - 1) / p.seg));
-    f32_stream_col_kernel<R><<<grid, 128, 0, s>>>(p);
+    ColKernel<R>::get()<<<grid, 128, 0, s>>>(p);
     return cudaGetLastError();
 }
 
@@ -272,8 +348,11 @@ bool f32_stream_supported(const F32Line& g, int radius)
     // 0.156 / 0.160 / 0.189 vs 0.245 / 0.253 / 0.296 (87-105 % of the measured copy bandwidth; with an
     // element-wise halo gather in the edge threads the 17-tap row pass took 0.352), column pass 0.170 / 0.19 /
     // 0.252 vs 0.23 / 0.24 / 0.27; 25 / 33 taps 0.34-0.67 vs 0.30-0.35: radius 12 / 16 stay on the tiles.
-    if (R > 8) return false;
     if (g.n_in <= 0 || g.n_out <= 0 || g.outer <= 0 || g.inner <= 0) return false;
+    // radius 9..16: the ROW kernel wins over the shared-memory tile (33 taps on 512^3: 0.290 vs 0.356 ms); the packed
+    // column kernel does not (0.59 vs 0.34 ms: ptxas sinks its prefetch ring next to the consumers — 62 % long-
+    // scoreboard stalls even with volatile loads), so wide column passes stay on the tiles
+    if (R > 8 && g.inner != 1) return false;
     const uintptr_t a = reinterpret_cast<uintptr_t>(g.in) | reinterpret_cast<uintptr_t>(g.out);
     if (g.inner == 1) {
         if (a & 3) return false;
@@ -310,9 +389,17 @@ cudaError_t launch_f32_stream(const F32Line& g, const F32Taps& t, cudaStream_t s
     case 2: return launch_fstream<2>(p, t, s);
     case 3: return launch_fstream<3>(p, t, s);
     case 4: return launch_fstream<4>(p, t, s);
+    case 5: return launch_fstream<5>(p, t, s);
     case 6: return launch_fstream<6>(p, t, s);
+    case 7: return launch_fstream<7>(p, t, s);
     case 8: return launch_fstream<8>(p, t, s);
+    case 9: return launch_fstream<9>(p, t, s);
+    case 10: return launch_fstream<10>(p, t, s);
+    case 11: return launch_fstream<11>(p, t, s);
     case 12: return launch_fstream<12>(p, t, s);
+    case 13: return launch_fstream<13>(p, t, s);
+    case 14: return launch_fstream<14>(p, t, s);
+    case 15: return launch_fstream<15>(p, t, s);
     case 16: return launch_fstream<16>(p, t, s);
     default: return cudaErrorInvalidValue;
     }

@@ -553,12 +553,10 @@ int radius_bucket(int r, bool has_z)
     // against 1.02 ms for three tiled passes.  Without one (stacks of 2-D images) the kernel carries no
     // z state and serves radius 12 and 16 with 2-plane groups.  (Tiled z pass + this kernel for the
     // y / x part of a 3-D filter: 1.04 ms on 512^3 sigma 4, no better than three tiled passes.)
-    static const int buckets[] = {1, 2, 3, 4, 6, 8};
-    for (int b : buckets) if (r <= b) return b;
-    if (!has_z) {
-        if (r <= 12) return 12;
-        if (r <= 16) return 16;
-    }
+    // one instantiation per radius, never a zero-padded wider one: 0 * NaN / 0 * Inf would spread a
+    // non-finite sample beyond the true footprint of the filter (scipy keeps those neighbours finite)
+    if (r >= 1 && r <= 8) return r;
+    if (!has_z && (r == 12 || r == 16)) return r;
     return -1;
 }
 
@@ -661,6 +659,13 @@ bool fused3d_supported(const FusedVolume& v, const F32Taps taps[3], bool gradmag
     for (int a = 0; a < 3; ++a) r = taps[a].radius > r ? taps[a].radius : r;
     const bool z_pass = !(taps[0].radius == 0 && taps[0].w[0] == 1.0f);
     if (radius_bucket(r, z_pass || gradmag) < 0) return false;   // gradient magnitude: one launch per axis, epilogue variants exist up to radius 8
+    // every filtered axis must have exactly the kernel's radius (no zero-padded taps, see radius_bucket); an
+    // unfiltered z axis has its own instantiation (HAS_Z = false), an unfiltered y or x axis has not
+    for (int a = 0; a < 3; ++a) {
+        const bool identity = taps[a].radius == 0 && taps[a].w[0] == 1.0f;
+        if (a == 0 && identity) continue;
+        if (taps[a].radius != r) return false;
+    }
     if (v.nx % 4 != 0 || (reinterpret_cast<uintptr_t>(v.in) & 15) || (reinterpret_cast<uintptr_t>(v.out) & 15))
         return false;
     if (v.nx < 1 || v.ny < 1 || v.nz_in < 1 || v.nz_out < 1) return false;
@@ -682,7 +687,7 @@ bool fused3d_supported(const FusedVolume& v, const F32Taps taps[3], bool gradmag
         // neighbour planes come through their own tensor maps: whole slab, a z pass, sources of every
         // x / y halo cell inside the tile, one launch (the accumulating gradient-magnitude launches are not
         // instantiated with halos: fused_ws serves that call)
-        if (!has_z || gradmag || v.z_offset != 0 || v.nz_in != v.nz_out || v.ny < 32 || v.nx < 32) return false;
+        if (!has_z || gradmag || v.z_offset < 0 || v.z_offset + v.nz_out > v.nz_in || v.ny < 32 || v.nx < 32) return false;
         if ((v.halo->lo && v.halo->planes_lo < taps[0].radius) || (v.halo->hi && v.halo->planes_hi < taps[0].radius))
             return false;
         if (v.nz_in < taps[0].radius) return false;
@@ -794,8 +799,12 @@ static cudaError_t launch_one(const FusedVolume& v, const F32Taps taps[3], int e
     case 3 * 2 + 1: return launch_r<3, true>(v, p, s);
     case 4 * 2 + 0: return launch_r<4, false>(v, p, s);
     case 4 * 2 + 1: return launch_r<4, true>(v, p, s);
+    case 5 * 2 + 0: return launch_r<5, false>(v, p, s);
+    case 5 * 2 + 1: return launch_r<5, true>(v, p, s);
     case 6 * 2 + 0: return launch_r<6, false>(v, p, s);
     case 6 * 2 + 1: return launch_r<6, true>(v, p, s);
+    case 7 * 2 + 0: return launch_r<7, false>(v, p, s);
+    case 7 * 2 + 1: return launch_r<7, true>(v, p, s);
     case 8 * 2 + 0: return launch_r<8, false>(v, p, s);
     case 8 * 2 + 1: return launch_r<8, true>(v, p, s);
     case 12 * 2 + 0: return launch_wide_xy<12>(v, p, s);

@@ -252,7 +252,7 @@ bool minmax_stream_supported(const ExactTiledGeom& g, int S, int origin, double 
     if (!(cval == cval)) return false;
     if (g.in_dtype != SEPFILT_F32 && g.in_dtype != SEPFILT_F64 && (cval <= lo - 1.0 || cval >= hi + 1.0)) return false;
     if (g.in_dtype == SEPFILT_F32 && (cval > 3.4028234663852886e38 || cval < -3.4028234663852886e38)) return false;
-    if (g.outer <= 0 || g.inner <= 0 || g.n_in <= 0 || g.n_in > 2147483647LL - 4096) return false;
+    if (g.outer <= 0 || g.inner <= 0 || g.n_in <= 0 || g.n_in > 1073741824LL /* 2n must fit an int in the boundary fold */) return false;
     const int es = dtype_size(g.in_dtype);
     const uintptr_t a = reinterpret_cast<uintptr_t>(g.in) | reinterpret_cast<uintptr_t>(g.out);
     if (g.inner == 1) {

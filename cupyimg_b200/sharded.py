@@ -83,6 +83,7 @@ class ZSlabFilter:
         self.slab = None
         self.epoch = 0
         self.p2p = False
+        self.last_backend = "none"        # how the last run got its halos (reported by bench.py)
         if backend != "nccl" and self.world > 1 and self.on_cuda and dtype == torch.float32 and r > 0:
             try:
                 self._init_p2p()
@@ -156,60 +157,87 @@ class ZSlabFilter:
         stream = _array.current_stream(self.device)
         lower, upper = self._peer(-1), self._peer(+1)
         epoch = self.epoch + 1
-        r = self.r
-        halo = _ffi.Halo()
+        self.epoch = epoch
+        r, nz = self.r, self.nz
         mine = self._flag_ptrs[self.rank]
         # the warp-specialised kernel (gradient magnitude) waits for a neighbour's flag only when its march reaches
         # that neighbour's planes and spreads the reads over its z segments: in place is faster there
         mode = self.p2p_mode if self.p2p_mode != "auto" else ("direct" if dspecs is not None else "pull")
-        pull = mode == "pull"
-        if self.has_lo:
-            halo.lo = self._pad_lo.data_ptr() if pull else self._slab_ptrs[lower] + (self.nz - r) * self._plane_bytes
-            halo.planes_lo = r
-            halo.ready_lo = None if pull else mine + 4 * _LO_READY
-        if self.has_hi:
-            halo.hi = self._pad_hi.data_ptr() if pull else self._slab_ptrs[upper]
-            halo.planes_hi = r
-            halo.ready_hi = None if pull else mine + 4 * _HI_READY
-        halo.epoch = epoch
-        # the kernel's last CTA tells the neighbours that their planes have been read (no stream operation
-        # after the launch): I am the lower rank's UPPER neighbour, so I set its HI_DONE flag
-        halo.cta_counter = mine + 4 * _CTA_COUNTER
-        if self.has_lo:
-            halo.done_lo = self._flag_ptrs[lower] + 4 * _HI_DONE
-        if self.has_hi:
-            halo.done_hi = self._flag_ptrs[upper] + 4 * _LO_DONE
+        grad = 1 if dspecs is not None else 0
         # my slab is complete at this point of the stream: tell the ranks that read it (one batched memop)
         _ffi.check(L.sepfilt_stream_write32x2(
             stream, self._flag_ptrs[lower] + 4 * _HI_READY if self.has_lo else None,
             self._flag_ptrs[upper] + 4 * _LO_READY if self.has_hi else None, epoch))
-        if pull:
-            # side stream: wait (stream memory operation, no SM) until a neighbour's slab is complete, then let a
-            # copy engine pull its r planes over NVLink; the launch waits for both pads
-            main = torch.cuda.current_stream(self.device)
-            sides = ((self.has_lo, self.comm_stream, _LO_READY, self._pad_lo, self._peer_lo),
-                     (self.has_hi, self.comm_stream2, _HI_READY, self._pad_hi, self._peer_hi))
-            for present, side, slot, pad, peer_planes in sides:      # one stream per side: two copy engines at once
-                if not present:
-                    continue
-                side.wait_stream(main)                               # the previous launch has finished reading the pad
-                with torch.cuda.stream(side):
-                    _ffi.check(L.sepfilt_stream_wait32_geq(_array.current_stream(self.device), mine + 4 * slot, epoch))
-                    pad.copy_(peer_planes, non_blocking=True)
-                main.wait_stream(side)
-        rc = L.sepfilt_separable_f32_halo(inp.tensor(), out.tensor(), arr, len(structs), darr,
-                                          1 if dspecs is not None else 0, ctypes.byref(halo), float(cval), stream)
-        self.epoch = epoch
-        ok = rc != _ffi.ERR_UNSUPPORTED
-        if ok:
+
+        def halo_launch(src, dst, halo, in_offset0):
+            rc = L.sepfilt_separable_f32_halo(_array.ingest(src).tensor(), _array.ingest(dst).tensor(), arr, len(structs),
+                                              darr, grad, ctypes.byref(halo), int(in_offset0), float(cval), stream)
+            if rc == _ffi.ERR_UNSUPPORTED:
+                return False
             _ffi.check(rc)
             _ffi.count_launch(1)
-        if not ok:
-            # nothing was launched: release the neighbours by hand (an unsupported request read nothing)
+            return True
+
+        if mode == "direct":
+            # ONE launch over the whole slab: TMA reads the neighbours' planes in place; the kernel's last CTA
+            # sets the neighbours' done flags (no stream operation after the launch)
+            halo = _ffi.Halo()
+            halo.epoch = epoch
+            halo.cta_counter = mine + 4 * _CTA_COUNTER
             if self.has_lo:
-                self._write_flag(lower, _HI_DONE, epoch, stream)
+                halo.lo, halo.planes_lo = self._slab_ptrs[lower] + (nz - r) * self._plane_bytes, r
+                halo.ready_lo = mine + 4 * _LO_READY
+                halo.done_lo = self._flag_ptrs[lower] + 4 * _HI_DONE       # I am the lower rank's UPPER neighbour
             if self.has_hi:
-                self._write_flag(upper, _LO_DONE, epoch, stream)
+                halo.hi, halo.planes_hi = self._slab_ptrs[upper], r
+                halo.ready_hi = mine + 4 * _HI_READY
+                halo.done_hi = self._flag_ptrs[upper] + 4 * _LO_DONE
+            ok = halo_launch(self.slab, output, halo, 0)
+            if ok:
+                self.last_backend = "peer memory: the fused kernel's TMA reads the neighbour planes in place over NVLink"
+            else:                                   # nothing was launched: release the neighbours by hand
+                if self.has_lo:
+                    self._write_flag(lower, _HI_DONE, epoch, stream)
+                if self.has_hi:
+                    self._write_flag(upper, _LO_DONE, epoch, stream)
+            return ok
+
+        # "pull": copy engines fetch the neighbours' r planes into local pads on side streams (a stream memory
+        # operation holds each copy until the neighbour's slab is complete — no SM involved), while the INTERIOR
+        # planes [r, nz - r), which need no halo, are filtered at once; the two r-plane boundary strips follow,
+        # each from the slab's first / last 2r planes plus one pad.  The whole exchange hides behind the interior.
+        main = torch.cuda.current_stream(self.device)
+        sides = ((self.has_lo, self.comm_stream, _LO_READY, self._pad_lo, self._peer_lo, lower, _HI_DONE),
+                 (self.has_hi, self.comm_stream2, _HI_READY, self._pad_hi, self._peer_hi, upper, _LO_DONE))
+        for present, side, slot, pad, peer_planes, peer, done_slot in sides:
+            if not present:
+                continue
+            side.wait_stream(main)                                   # the previous strip launch has finished reading the pad
+            with torch.cuda.stream(side):
+                cs = _array.current_stream(self.device)
+                _ffi.check(L.sepfilt_stream_wait32_geq(cs, mine + 4 * slot, epoch))
+                pad.copy_(peer_planes, non_blocking=True)
+                # the neighbour's planes have been read: it may overwrite its slab
+                _ffi.check(L.sepfilt_stream_write32(cs, self._flag_ptrs[peer] + 4 * done_slot, epoch))
+        z0 = r if self.has_lo else 0
+        z1 = nz - r if self.has_hi else nz
+        ok = True
+        if z1 > z0:
+            ok = _filters._try_fused(_array.ingest(self.slab), _array.ingest(output[z0:z1]), specs, cval,
+                                     dspecs=dspecs, in_offset0=z0)
+        if ok and self.has_lo:
+            main.wait_stream(self.comm_stream)
+            halo = _ffi.Halo()
+            halo.lo, halo.planes_lo = self._pad_lo.data_ptr(), r
+            ok = halo_launch(self.slab[:2 * r], output[:r], halo, 0)
+        if ok and self.has_hi:
+            main.wait_stream(self.comm_stream2)
+            halo = _ffi.Halo()
+            halo.hi, halo.planes_hi = self._pad_hi.data_ptr(), r
+            ok = halo_launch(self.slab[nz - 2 * r:], output[nz - r:], halo, r)
+        if ok:
+            self.last_backend = ("peer memory: copy engines pull the neighbour planes over NVLink behind the interior launch, "
+                                 "boundary strips from slab + pad")
         return ok
 
     def _try_p2p(self, x, output, specs, dspecs, dtype_mode):
@@ -262,6 +290,7 @@ class ZSlabFilter:
             return output
         z0 = r if self.has_lo else 0
         z1 = nz - r if self.has_hi else nz
+        self.last_backend = "nccl send/recv of raw halo planes overlapped with the interior launches"
         if self.on_cuda:
             main = torch.cuda.current_stream(self.device)
             self.comm_stream.wait_stream(main)            # x must be complete before it is sent

@@ -180,13 +180,16 @@ typedef struct {
     uint32_t        reserved;
 } sepfilt_halo;
 
-/* sepfilt_separable_f32 on a z-slab with neighbour halos (rank-3 float32, in and out of equal shape,
- * a z pass present).  SEPFILT_ERR_UNSUPPORTED when no fused kernel takes the request: the caller then
- * exchanges halos into a local buffer and uses the windowed call. */
+/* sepfilt_separable_f32 on a z-slab with neighbour halos (rank-3 float32, a z pass present).  `out` may be a
+ * window of `in` along axis 0 as in sepfilt_separable_f32 (out plane z <-> in plane z + in_offset0,
+ * 0 <= in_offset0, in_offset0 + out planes <= in planes): the r-plane boundary strips of a slab are filtered
+ * from its first / last 2r planes plus one neighbour's halo while the interior runs without any halo.
+ * SEPFILT_ERR_UNSUPPORTED when no fused kernel takes the request: the caller then exchanges halos into a
+ * local buffer and uses the windowed call. */
 SEPFILT_API int sepfilt_separable_f32_halo(const sepfilt_tensor* in, const sepfilt_tensor* out,
                                const sepfilt_pass* passes, int npasses,
                                const sepfilt_pass* dpasses, int gradient_magnitude,
-                               const sepfilt_halo* halo, double cval, void* stream);
+                               const sepfilt_halo* halo, int64_t in_offset0, double cval, void* stream);
 
 /* Stream-ordered 32-bit flag operations (cuStreamWriteValue32 / cuStreamWaitValue32, no kernel, no SM):
  * write `value` to *addr when the stream reaches this point (addr may be peer-mapped), or hold the

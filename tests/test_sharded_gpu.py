@@ -1,6 +1,7 @@
-"""z-slab sharding on real GPUs (NCCL halo exchange): sharded result == single-GPU result,
-bit for bit, for every boundary mode.  Needs >= 2 GPUs (skipped otherwise); on one GPU the
-world-size-1 plan is still exercised."""
+"""z-slab sharding on real GPUs: sharded result == single-GPU result, bit for bit, for every boundary mode and
+for both halo backends (peer memory: neighbour planes pulled by copy engines / read in place by TMA from
+symmetric memory; NCCL send/recv).  Needs >= 2 GPUs (skipped otherwise); on one GPU the world-size-1 plan is
+still exercised and tests/test_halo_gpu.py covers the halo entry point with local stand-ins."""
 import os
 import socket
 
@@ -18,7 +19,7 @@ def _free_port():
     return port
 
 
-def _worker(rank, world, port, result_dir):
+def _worker(rank, world, port, result_dir, backend):
     import torch
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -37,15 +38,23 @@ def _worker(rank, world, port, result_dir):
             for sigma, radius in [(2.0, 8), (1.0, 4)]:
                 want = ndi.gaussian_filter(vol.to(dev), sigma, mode=mode)
                 x = vol[rank * nz:(rank + 1) * nz].to(dev)
-                plan = sharded.ZSlabFilter(x.shape, radius=radius, mode=mode, device=dev)
+                plan = sharded.ZSlabFilter(x.shape, radius=radius, mode=mode, device=dev, backend=backend)
                 got = plan.gaussian_filter(x, sigma)
                 torch.cuda.synchronize()
                 ok = ok and torch.equal(got, want[rank * nz:(rank + 1) * nz])
+                if backend == "p2p" and mode != "wrap":
+                    ok = ok and plan.last_backend.startswith("peer memory")
+                    # a second and third step through the same plan, the slab refilled in place in between
+                    plan.begin_fill()
+                    plan.slab.copy_(x * 0.5)
+                    got_b = plan.gaussian_filter(plan.slab, sigma)
+                    torch.cuda.synchronize()
+                    ok = ok and torch.equal(got_b, ndi.gaussian_filter(vol.to(dev) * 0.5, sigma, mode=mode)[rank * nz:(rank + 1) * nz])
                 got2 = plan.uniform_filter(x, 5)
                 want2 = ndi.uniform_filter(vol.to(dev), 5, mode=mode)
                 ok = ok and torch.equal(got2, want2[rank * nz:(rank + 1) * nz])
             # C4's filter: three derivative filters behind one halo exchange
-            plan = sharded.ZSlabFilter(x.shape, radius=6, mode=mode, device=dev)
+            plan = sharded.ZSlabFilter(x.shape, radius=6, mode=mode, device=dev, backend=backend)
             got3 = plan.gaussian_gradient_magnitude(x, 1.5)
             want3 = ndi.gaussian_gradient_magnitude(vol.to(dev), 1.5, mode=mode)
             ok = ok and torch.equal(got3, want3[rank * nz:(rank + 1) * nz])
@@ -54,7 +63,7 @@ def _worker(rank, world, port, result_dir):
             ok = ok and torch.equal(got4, want4[rank * nz:(rank + 1) * nz])
             # exact (float64-accumulate) staging of the same filter on an integer volume
             vi = (vol * 1000).to(torch.int32)
-            plan_i = sharded.ZSlabFilter(x.shape, radius=6, mode=mode, device=dev, dtype=torch.int32)
+            plan_i = sharded.ZSlabFilter(x.shape, radius=6, mode=mode, device=dev, dtype=torch.int32, backend="auto")
             got5 = plan_i.gaussian_gradient_magnitude(vi[rank * nz:(rank + 1) * nz].to(dev), 1.5)
             want5 = ndi.gaussian_gradient_magnitude(vi.to(dev), 1.5, mode=mode)
             ok = ok and torch.equal(got5, want5[rank * nz:(rank + 1) * nz])
@@ -64,14 +73,15 @@ def _worker(rank, world, port, result_dir):
         dist.destroy_process_group()
 
 
-def test_zslab_nccl_matches_single_gpu(tmp_path):
+@pytest.mark.parametrize("backend", ["p2p", "nccl"])
+def test_zslab_matches_single_gpu(tmp_path, backend):
     import torch
     import torch.multiprocessing as mp
     n = torch.cuda.device_count()
     if n < 2:
         pytest.skip("needs >= 2 GPUs")
     world = 2
-    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path), backend), nprocs=world, join=True)
     for r in range(world):
         assert (tmp_path / ("rank%d" % r)).read_text() == "ok"
 

@@ -26,7 +26,7 @@ def halo_call(x, lo, hi, out, specs, dspecs=None, flags=None, epoch=0):
     if flags is not None:
         h.ready_lo, h.ready_hi, h.epoch = flags.data_ptr(), flags.data_ptr() + 4, epoch
     rc = _ffi.lib().sepfilt_separable_f32_halo(inp.tensor(), o.tensor(), arr, len(structs), darr, 1 if dspecs is not None else 0,
-                                               ctypes.byref(h), 0.0, _array.current_stream(x.device))
+                                               ctypes.byref(h), 0, 0.0, _array.current_stream(x.device))
     _ffi.check(rc)
 
 
