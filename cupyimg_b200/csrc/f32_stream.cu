@@ -228,7 +228,7 @@ f32_stream_row_kernel(const __grid_constant__ FStreamParams p)
     // Aligned rows (the common case): the halo of the first / last thread of a row is the mirror image of
     // elements the thread already holds, so it is filled by register selects instead of an element-wise
     // gather (which cost a second round of dependent loads in every warp holding an edge thread).
-    const bool reg_edges = vec_ok && p.shift == 0 && p.n_in == p.n_out && (p.n_in & 7) == 0 && p.n_in >= 8 * H + 8 &&
+    const bool reg_edges = vec_ok && p.shift == 0 && p.n_in == p.n_out && (p.n_in & 7) == 0 && p.n_in >= 16 * H &&
                            p.mode != SEPFILT_WRAP;
     float win[4 * NW];
 #pragma unroll
@@ -249,18 +249,23 @@ f32_stream_row_kernel(const __grid_constant__ FStreamParams p)
     }
     if (reg_edges && p.mode != SEPFILT_CONSTANT) {
         const int e = p.mode == SEPFILT_REFLECT ? 1 : 0;     // reflect: d c b a | a b c d ; mirror: d c b | a b c d
-        if (x == 0) {                                        // win[i], i < 4H, is array column i - 4H
+        // a thread 8 d columns away from a row end (d = 0 .. (4H-1)/8) holds out-of-array window entries whose
+        // sources it also holds: win[i] is array column x + i - 4H
 #pragma unroll
-            for (int i = 0; i < 4 * H; ++i) {
-                const float refl = win[8 * H - 1 - i], mirr = win[8 * H - i];
-                win[i] = p.mode == SEPFILT_NEAREST ? win[4 * H] : (e ? refl : mirr);
+        for (int d = 0; 8 * d < 4 * H; ++d) {
+            if (x == 8 * d) {                                // entries i < 4H - 8d lie left of column 0
+#pragma unroll
+                for (int i = 0; i < 4 * H - 8 * d; ++i) {
+                    const float refl = win[8 * H - 16 * d - 1 - i], mirr = win[8 * H - 16 * d - i];
+                    win[i] = p.mode == SEPFILT_NEAREST ? win[4 * H - 8 * d] : (e ? refl : mirr);
+                }
             }
-        }
-        if (x + FROW_P == p.n_in) {                          // win[i], i >= 4H + 8, is array column n + (i - 4H - 8)
+            if (x + FROW_P + 8 * d == p.n_in) {              // entries i >= 4H + 8 + 8d lie right of column n - 1
 #pragma unroll
-            for (int i = 4 * H + 8; i < 8 * H + 8; ++i) {
-                const float refl = win[8 * H + 15 - i], mirr = win[8 * H + 14 - i];
-                win[i] = p.mode == SEPFILT_NEAREST ? win[4 * H + 7] : (e ? refl : mirr);
+                for (int i = 4 * H + 8 + 8 * d; i < 8 * H + 8; ++i) {
+                    const float refl = win[8 * H + 15 + 16 * d - i], mirr = win[8 * H + 14 + 16 * d - i];
+                    win[i] = p.mode == SEPFILT_NEAREST ? win[4 * H + 7 + 8 * d] : (e ? refl : mirr);
+                }
             }
         }
     }

@@ -429,9 +429,10 @@ def test_host_pipeline_matches_resident_filter(ndi):
 
 @pytest.mark.parametrize("mode", ["reflect", "constant", "nearest", "mirror", "wrap"])
 def test_f32_radius_9_to_16(mode, ndi):
-    """sigma 2.5 .. 4 (radius 10 .. 16).  3-D volumes: three tiled passes (the fused kernel keeps no z state
+    """sigma 2.5 .. 4 (radius 10 .. 16).  3-D volumes: three single-axis passes (the fused kernel keeps no z state
     at that radius; z pass + fused y/x was measured at 1.04 ms against 1.02 ms on 512^3 and dropped).
-    Stacks of 2-D images (no z pass): ONE fused launch through the radius 12 / 16 buckets."""
+    Stacks of 2-D images (no z pass): ONE fused launch at radius 12 / 16 (the instantiated radii — taps are never
+    zero-padded to a wider kernel, tests/test_nonfinite_gpu.py), two single-axis passes at radius 10."""
     from cupyimg_b200 import _ffi
     rng = np.random.default_rng(33)
     for shape, sig, launches in [((40, 52, 64), lambda s: s, 3), ((12, 70, 200), lambda s: (0, s, s), 1)]:
@@ -443,6 +444,8 @@ def test_f32_radius_9_to_16(mode, ndi):
             got = to_host(ndi.gaussian_filter(xd, sig(sigma), mode=mode))
             # wrap along y / x is declined by the fused kernel (far-side sources): per-axis passes
             expect = len(shape) - (1 if launches == 1 else 0) if mode == "wrap" else launches
+            if launches == 1 and sigma == 2.5:
+                expect = 2
             assert _ffi.LAUNCHES == expect, (shape, sigma, _ffi.LAUNCHES)
             assert_f32_close(got, want, atol_scale=2e-6)
 
