@@ -17,6 +17,7 @@
 #include <cstdlib>
 #include "common.cuh"
 #include "kernels.h"
+#include "ptx.cuh"
 
 namespace sepfilt {
 
@@ -132,12 +133,24 @@ corr1d_f32_col_kernel(const __grid_constant__ F32Line g, const __grid_constant__
     if (vec) {
         const int lane16 = tid & 15;
         const int64_t ii = i0 + 4 * lane16;
-        for (int e = tid >> 4; e < rows_needed; e += 16) {
-            const int m = remap_index32(g.mode, src0 + e, g.n_in);
-            float4 v = make_float4(g.cval, g.cval, g.cval, g.cval);
-            if (m >= 0 && ii < g.inner)
-                v = __ldg(reinterpret_cast<const float4*>(base_in + (int64_t)m * g.inner + ii));
-            *reinterpret_cast<float4*>(&tile[e][4 * lane16]) = v;
+        // all loads of a thread are issued before its first store: the staging phase costs one memory round
+        // trip instead of one per 16 rows (the rolled loop exposed ROWS / 16 dependent latencies per CTA)
+        constexpr int NIT = (ROWS + 15) / 16;
+        float4 v[NIT];
+#pragma unroll
+        for (int it = 0; it < NIT; ++it) {
+            const int e = (tid >> 4) + 16 * it;
+            v[it] = make_float4(g.cval, g.cval, g.cval, g.cval);
+            if (e < rows_needed) {
+                const int m = remap_index32(g.mode, src0 + e, g.n_in);
+                if (m >= 0 && ii < g.inner)
+                    v[it] = __ldg(reinterpret_cast<const float4*>(base_in + (int64_t)m * g.inner + ii));
+            }
+        }
+#pragma unroll
+        for (int it = 0; it < NIT; ++it) {
+            const int e = (tid >> 4) + 16 * it;
+            if (e < rows_needed) *reinterpret_cast<float4*>(&tile[e][4 * lane16]) = v[it];
         }
     } else {
         const int lane64 = tid & 63;
@@ -156,23 +169,28 @@ corr1d_f32_col_kernel(const __grid_constant__ F32Line g, const __grid_constant__
     const int64_t ii = i0 + 4 * ti;
     const int p0 = n0 + tn * COL_RN;
     if (ii >= g.inner || p0 >= g.n_out) return;
-    float4 acc[COL_RN];
+    // packed fma.rn.f32x2 on the two column pairs of the lane's float4, scalar-broadcast tap: half the issue
+    // slots of four scalar FFMA per row and tap (same products, same summation order)
+    ptx::u64 acc2[COL_RN][2];
 #pragma unroll
-    for (int q = 0; q < COL_RN; ++q) acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int q = 0; q < COL_RN; ++q) acc2[q][0] = acc2[q][1] = 0ull;
 #pragma unroll
     for (int j = 0; j < COL_RN + 2 * R; ++j) {
-        const float4 v = *reinterpret_cast<const float4*>(&tile[tn * COL_RN + j][4 * ti]);
+        const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(&tile[tn * COL_RN + j][4 * ti]);
 #pragma unroll
         for (int q = 0; q < COL_RN; ++q) {
             const int k = j - q;
             if (k >= 0 && k <= 2 * R) {
-                const float w = t.w[k];
-                acc[q].x = fmaf(w, v.x, acc[q].x);
-                acc[q].y = fmaf(w, v.y, acc[q].y);
-                acc[q].z = fmaf(w, v.z, acc[q].z);
-                acc[q].w = fmaf(w, v.w, acc[q].w);
+                acc2[q][0] = ptx::fma2s(v.x, t.w[k], acc2[q][0]);
+                acc2[q][1] = ptx::fma2s(v.y, t.w[k], acc2[q][1]);
             }
         }
+    }
+    float4 acc[COL_RN];
+#pragma unroll
+    for (int q = 0; q < COL_RN; ++q) {
+        ptx::unpack2(acc2[q][0], acc[q].x, acc[q].y);
+        ptx::unpack2(acc2[q][1], acc[q].z, acc[q].w);
     }
 #pragma unroll
     for (int q = 0; q < COL_RN; ++q) {

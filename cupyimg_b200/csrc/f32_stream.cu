@@ -269,6 +269,9 @@ f32_stream_row_kernel(const __grid_constant__ FStreamParams p)
             }
         }
     }
+    // (packed fma.rn.f32x2 on output pairs with re-paired window copies was measured here: 17 taps 0.189 -> 0.225 ms,
+    // 33 taps 0.298 -> 0.386 ms on 512^3 — the second copy of the window costs the occupancy the halved issue
+    // slots would have bought)
     float acc[FROW_P];
 #pragma unroll
     for (int o = 0; o < FROW_P; ++o) acc[o] = win[OFF + o] * p.w[0];

@@ -556,7 +556,9 @@ int radius_bucket(int r, bool has_z)
     // one instantiation per radius, never a zero-padded wider one: 0 * NaN / 0 * Inf would spread a
     // non-finite sample beyond the true footprint of the filter (scipy keeps those neighbours finite)
     if (r >= 1 && r <= 8) return r;
-    if (!has_z && (r == 12 || r == 16)) return r;
+    // radius 12 / 16 without a z pass (stacks of 2-D images) used to run here (launch_wide_xy): 0.706 ms for
+    // sigma (0, 4, 4) on 512^3, against 0.242 + 0.299 ms for the two single-axis passes it replaces
+    (void)has_z;
     return -1;
 }
 
@@ -763,14 +765,6 @@ cudaError_t launch_r(const FusedVolume& v, FusedParams& p, cudaStream_t s)
 }  // namespace
 
 // y + x only, radius 12 / 16: one configuration (128-wide tiles, 2-plane groups, no epilogue variants)
-template <int R>
-cudaError_t launch_wide_xy(const FusedVolume& v, FusedParams& p, cudaStream_t s)
-{
-    const int sms = cached_sm_count();
-    plan_tiles(v, R, false, 128, sms, &p);
-    return launch_e<R, false, Cfg<R, 128, 2, 1>, false>(p, s);
-}
-
 static cudaError_t launch_one(const FusedVolume& v, const F32Taps taps[3], int epilogue_mode, cudaStream_t s)
 {
     int r = 0;
@@ -807,8 +801,6 @@ static cudaError_t launch_one(const FusedVolume& v, const F32Taps taps[3], int e
     case 7 * 2 + 1: return launch_r<7, true>(v, p, s);
     case 8 * 2 + 0: return launch_r<8, false>(v, p, s);
     case 8 * 2 + 1: return launch_r<8, true>(v, p, s);
-    case 12 * 2 + 0: return launch_wide_xy<12>(v, p, s);
-    case 16 * 2 + 0: return launch_wide_xy<16>(v, p, s);
     default: return cudaErrorInvalidValue;
     }
 }

@@ -431,11 +431,11 @@ def test_host_pipeline_matches_resident_filter(ndi):
 def test_f32_radius_9_to_16(mode, ndi):
     """sigma 2.5 .. 4 (radius 10 .. 16).  3-D volumes: three single-axis passes (the fused kernel keeps no z state
     at that radius; z pass + fused y/x was measured at 1.04 ms against 1.02 ms on 512^3 and dropped).
-    Stacks of 2-D images (no z pass): ONE fused launch at radius 12 / 16 (the instantiated radii — taps are never
-    zero-padded to a wider kernel, tests/test_nonfinite_gpu.py), two single-axis passes at radius 10."""
+    Stacks of 2-D images (no z pass): two single-axis passes as well (the fused 2-D kernel for radius 12 / 16 was
+    dropped when the single-axis passes overtook it: 0.54 against 0.71 ms for sigma (0, 4, 4) on 512^3)."""
     from cupyimg_b200 import _ffi
     rng = np.random.default_rng(33)
-    for shape, sig, launches in [((40, 52, 64), lambda s: s, 3), ((12, 70, 200), lambda s: (0, s, s), 1)]:
+    for shape, sig, launches in [((40, 52, 64), lambda s: s, 3), ((12, 70, 200), lambda s: (0, s, s), 2)]:
         x = rng.random(shape).astype(np.float32)
         xd = to_device(x)
         for sigma in (2.5, 3.0, 4.0):
@@ -443,9 +443,7 @@ def test_f32_radius_9_to_16(mode, ndi):
             _ffi.LAUNCHES = 0
             got = to_host(ndi.gaussian_filter(xd, sig(sigma), mode=mode))
             # wrap along y / x is declined by the fused kernel (far-side sources): per-axis passes
-            expect = len(shape) - (1 if launches == 1 else 0) if mode == "wrap" else launches
-            if launches == 1 and sigma == 2.5:
-                expect = 2
+            expect = launches
             assert _ffi.LAUNCHES == expect, (shape, sigma, _ffi.LAUNCHES)
             assert_f32_close(got, want, atol_scale=2e-6)
 
