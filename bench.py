@@ -606,7 +606,30 @@ def run_ours(args):
         e2e_equal = t[1].item() == 0.0
     e2e_value = voxels * e2e_steps / e2e_s / 1e9
     parity["e2e_equals_device_result"] = e2e_equal
-    del hx, hy
+    # the bound of this path: the same bytes as plain concurrent H2D + D2H copies on two streams, no kernels
+    s_h2d, s_d2h = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    dbuf_in = torch.empty(tuple(hx.shape), dtype=torch.float32, device=dev)
+    dbuf_out = torch.empty((NZ, NY, NX), dtype=torch.float32, device=dev)
+
+    def copy_step():
+        with torch.cuda.stream(s_h2d):
+            dbuf_in.copy_(hx, non_blocking=True)
+        with torch.cuda.stream(s_d2h):
+            hy.copy_(dbuf_out, non_blocking=True)
+
+    copy_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        copy_step()
+    barrier()
+    copy_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([copy_s], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        copy_s = float(t.item())
+    copy_only_value = voxels * e2e_steps / copy_s / 1e9
+    del hx, hy, dbuf_in, dbuf_out
 
     # ---- strong-scaling legs (BASELINE.json configs[2..4]) ----
     legs = {}
@@ -667,6 +690,9 @@ def run_ours(args):
                     "h2d_bytes_per_step": int((NZ * world + 2 * RADIUS * (world - 1)) * NY * NX * 4),
                     "d2h_bytes_per_step": NZ * NY * NX * 4 * world,
                     "steps": e2e_steps,
+                    "copy_only": {"value": copy_only_value, "unit": UNIT, "frac": e2e_value / copy_only_value,
+                                  "what": "the same H2D + D2H bytes as plain concurrent copies on two streams, no kernel: "
+                                          "the PCIe / host-memory bound of this path on this box"},
                     "api": "cupyimg_b200.host.gaussian_filter_host (pinned host in / out, 32-plane chunks, halos filled "
                            "device-to-device, 3 streams)" + ("" if world == 1 else
                            "; every rank streams its slab of the host volume with 8 overlap planes per side (host.slab_window)")},

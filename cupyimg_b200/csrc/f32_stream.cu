@@ -1,20 +1,12 @@
-// f32_stream.cu — register-streaming single-axis float32 passes (float32 in, float32 FMA accumulate,
-// float32 out): correlate1d / convolve1d / gaussian_filter1d on float32 arrays, the per-axis passes of
-// 3-D filters the fused kernel declines (radius > 8 with a z pass, wrap along y / x, cval != 0).
-// Same arithmetic contract as f32_1d.cu (rtol 1e-5 of scipy); what changes is the data movement — no
-// shared memory, no CTA barrier, every element loaded from DRAM once:
-//   f32_stream_col_kernel  filtered axis strided: a thread owns C adjacent columns (one 8- or 16-byte
-//       load per row) and marches a segment of the axis; every input row is scattered at once into 2R+1
-//       per-column accumulators that shift by one output per step.  The loop is unrolled by 2R+1 so the
-//       accumulator of logical index j at step s is physical slot (j + s) mod (2R+1): in-place updates, no
-//       register moves.  The rows of the next P steps are in flight in a register ring (slot reloaded right
-//       after it is consumed).  Segments are sized to whole waves of the resident CTAs.
-//   f32_stream_row_kernel  contiguous axis: a thread loads the two 16-byte chunks of its 8 outputs plus the
-//       halo chunks on either side straight from global memory (its neighbours' chunks: L1 hits) and stores
-//       two 16-byte vectors; chunks that are not fully inside the row are gathered element-wise through the
-//       boundary rule (_util.py:170-228), which only the edge threads of a row do.
-// Geometries these kernels do not take (unaligned pointers, inner extents that are not a multiple of the
-// column vector) stay on the shared-memory tiles of f32_1d.cu.
+// f32_stream.cu — register-streaming contiguous-axis float32 pass (float32 in, float32 FMA accumulate, float32
+// out): correlate1d / convolve1d / gaussian_filter1d along the last axis of float32 arrays, and the x pass of
+// 3-D filters the fused kernels decline (radius > 8 with a z pass, mixed radii, wrap along y / x, cval != 0).
+// Same arithmetic contract as f32_1d.cu (rtol 1e-5 of scipy); no shared memory, no CTA barrier:
+//   f32_stream_row_kernel  a thread loads the two 16-byte chunks of its 8 outputs plus the halo chunks on either
+//       side straight from global memory (its neighbours' chunks: L1 hits) and stores two 16-byte vectors; on
+//       aligned rows the out-of-array entries of the threads near a row end are filled by register selects from
+//       entries the thread already holds, otherwise element-wise through the boundary rule (_util.py:170-228).
+// Strided-axis passes and unaligned geometries run on the shared-memory tiles of f32_1d.cu.
 #include "common.cuh"
 #include "kernels.h"
 #include "ptx.cuh"
@@ -53,159 +45,10 @@ __device__ __forceinline__ int fremap_fast(int mode, int ix, int n)
     return fremap_outside(mode, ix, n);
 }
 
-template <int C> struct alignas(4 * C) FPack { float v[C]; };
-
-// ---- column kernel geometry: columns per thread, prefetch ring (a divisor of 2R+1) ----
-template <int R> struct FColGeom {
-    static constexpr int W = 2 * R + 1;
-    static constexpr int C = R <= 6 ? 4 : 2;      // 13 taps: 0.210 -> 0.197 ms with 4 columns; 17 taps spill at 4 (0.251 -> 0.375 ms)
-    static constexpr int ring()
-    {
-        int best = 1;
-        for (int p = 1; p <= W; ++p)
-            if (W % p == 0 && p * C <= 52) best = p;          // largest divisor of W within the register budget
-        return best;
-    }
-    static constexpr int P = ring();
-    static constexpr int REGS = W * C + P * C + 48;
-    static constexpr int CTAS = REGS <= 76 ? 6 : (REGS <= 92 ? 5 : (REGS <= 120 ? 4 : 3));
-};
-
-template <int R>
-__global__ void __launch_bounds__(128, (FColGeom<R>::CTAS))
-f32_stream_col_kernel(const __grid_constant__ FStreamParams p)
-{
-    typedef FColGeom<R> G;
-    constexpr int W = G::W, C = G::C, P = G::P;
-    typedef FPack<C> V;
-    const int64_t bx = blockIdx.x;
-    const int64_t o = bx / p.xblocks;
-    const int64_t col = ((bx - o * p.xblocks) * 128 + threadIdx.x) * C;
-    if (col >= p.inner) return;
-    const int p0 = blockIdx.y * p.seg;
-    const int p_end = min(p0 + p.seg, p.n_out);
-    const float* __restrict__ in = p.in + o * (int64_t)p.n_in * p.inner + col;
-    float* __restrict__ out = p.out + o * (int64_t)p.n_out * p.inner + col;
-    // input rows q0 .. q0 + (p_end - p0) + 2R - 1 are consumed in order; the output finished by input
-    // row q is p = q - shift - R
-    const int q0 = p0 + p.shift - R;
-    const int n_steps = (p_end - p0) + 2 * R;
-
-    auto fetch = [&](int q) -> V {                           // one row of this thread's columns (uniform remap)
-        V v;
-        const int m = fremap_fast(p.mode, q, p.n_in);
-        if (m < 0) {
-#pragma unroll
-            for (int c = 0; c < C; ++c) v.v[c] = p.cval;
-        } else {
-            v = *reinterpret_cast<const V*>(in + (int64_t)m * p.inner);
-        }
-        return v;
-    };
-    V pre[P];
-#pragma unroll
-    for (int i = 0; i < P; ++i) pre[i] = fetch(q0 + i);
-    float acc[W][C];
-#pragma unroll
-    for (int j = 0; j < W; ++j)
-#pragma unroll
-        for (int c = 0; c < C; ++c) acc[j][c] = 0.f;
-
-    for (int base = 0; base < n_steps; base += W) {
-        const bool interior = q0 + base >= 0 && q0 + base + W + P <= p.n_in && base + W <= n_steps;
-#pragma unroll
-        for (int s = 0; s < W; ++s) {
-            const int t = base + s;
-            if (!interior && t >= n_steps) break;
-            const V v = pre[s % P];
-            // slot reloaded right after it is consumed: prefetch distance P rows
-            if (interior) pre[s % P] = *reinterpret_cast<const V*>(in + (int64_t)(q0 + t + P) * p.inner);
-            else if (t + P < n_steps) pre[s % P] = fetch(q0 + t + P);
-            // logical accumulator j lives in slot (j + s) % W at step s of a block (in place, no moves)
-#pragma unroll
-            for (int j = 0; j < 2 * R; ++j)
-#pragma unroll
-                for (int c = 0; c < C; ++c)
-                    acc[(j + 1 + s) % W][c] = fmaf(v.v[c], p.w[2 * R - j], acc[(j + 1 + s) % W][c]);
-#pragma unroll
-            for (int c = 0; c < C; ++c) acc[s % W][c] = v.v[c] * p.w[0];
-            if (t >= 2 * R) {                                // logical accumulator 0 of the NEXT step is complete
-                V r;
-#pragma unroll
-                for (int c = 0; c < C; ++c) r.v[c] = acc[(s + 1) % W][c];
-                *reinterpret_cast<V*>(out + (int64_t)(p0 + t - 2 * R) * p.inner) = r;
-            }
-        }
-    }
-}
-
-// ---- column kernel for wide filters (radius 9..16): two columns per thread as ONE packed register pair, every
-// update a packed fma.rn.f32x2 with a scalar-broadcast tap.  The scalar version above unrolls to (2R+1)^2 * 2
-// FFMA — 35 KB of code at radius 16, more than the instruction cache holds (measured 0.34-0.67 ms per 512^3
-// pass); packed it is half of that and stays resident.
-template <int R> struct FCol2Geom {
-    static constexpr int W = 2 * R + 1;
-    static constexpr int ring()
-    {
-        int best = 1;
-        for (int p = 1; p <= W; ++p)
-            if (W % p == 0 && p <= 13) best = p;              // largest divisor of W up to 13 rows in flight
-        return best;
-    }
-    static constexpr int P = ring();
-};
-
-template <int R>
-__global__ void __launch_bounds__(128, 3)
-f32_stream_col2_kernel(const __grid_constant__ FStreamParams p)
-{
-    using ptx::u64;
-    typedef FCol2Geom<R> G;
-    constexpr int W = G::W, P = G::P;
-    const int64_t bx = blockIdx.x;
-    const int64_t o = bx / p.xblocks;
-    const int64_t col = ((bx - o * p.xblocks) * 128 + threadIdx.x) * 2;
-    if (col >= p.inner) return;
-    const int p0 = blockIdx.y * p.seg;
-    const int p_end = min(p0 + p.seg, p.n_out);
-    const float* __restrict__ in = p.in + o * (int64_t)p.n_in * p.inner + col;
-    float* __restrict__ out = p.out + o * (int64_t)p.n_out * p.inner + col;
-    const int q0 = p0 + p.shift - R;
-    const int n_steps = (p_end - p0) + 2 * R;
-
-    auto fetch = [&](int q) -> u64 {
-        const int m = fremap_fast(p.mode, q, p.n_in);
-        if (m < 0) return ptx::pack2(p.cval, p.cval);
-        return *reinterpret_cast<const u64*>(in + (int64_t)m * p.inner);
-    };
-    u64 pre[P];
-#pragma unroll
-    for (int i = 0; i < P; ++i) pre[i] = fetch(q0 + i);
-    u64 acc[W];
-#pragma unroll
-    for (int j = 0; j < W; ++j) acc[j] = 0ull;
-
-    for (int base = 0; base < n_steps; base += W) {
-        const bool interior = q0 + base >= 0 && q0 + base + W + P <= p.n_in && base + W <= n_steps;
-#pragma unroll
-        for (int s = 0; s < W; ++s) {
-            const int t = base + s;
-            if (!interior && t >= n_steps) break;
-            const u64 v = pre[s % P];
-            // volatile: the load must be ISSUED here, P rows ahead of its use (ptxas otherwise sinks it next to
-            // the consumer and every step waits for DRAM: 62 % long-scoreboard stalls)
-            if (interior) asm volatile("ld.global.nc.b64 %0, [%1];" : "=l"(pre[s % P]) : "l"(in + (int64_t)(q0 + t + P) * p.inner));
-            else if (t + P < n_steps) pre[s % P] = fetch(q0 + t + P);
-            // logical accumulator j lives in slot (j + s) % W at step s of a block (in place, no moves)
-#pragma unroll
-            for (int j = 0; j < 2 * R; ++j)
-                acc[(j + 1 + s) % W] = ptx::fma2s(v, p.w[2 * R - j], acc[(j + 1 + s) % W]);
-            acc[s % W] = ptx::mul2s(v, p.w[0]);
-            if (t >= 2 * R)
-                *reinterpret_cast<u64*>(out + (int64_t)(p0 + t - 2 * R) * p.inner) = acc[(s + 1) % W];
-        }
-    }
-}
+// (Column kernels lived here until round 2: per-thread rotating accumulators with a register prefetch ring, 4 or 2
+//  columns per thread.  Once the shared-memory tile kernel of f32_1d.cu issued all its staging loads before the
+//  first store and filtered with packed FFMA2, the tile won at every radius — 512^3 column pass, 9 / 17 / 33 taps:
+//  0.171 / 0.181 / 0.232 ms against 0.19 / 0.251 / 0.59 ms here — and the streaming column kernels were removed.)
 
 // ---- row kernel ----
 constexpr int FROW_P = 8;            // outputs per thread
@@ -299,17 +142,6 @@ int fstream_bucket(int r)
     return (r >= 1 && r <= 16) ? r : -1;
 }
 
-int fcols(int R) { return R <= 6 ? 4 : 2; }
-
-template <int R> struct ColKernel {
-    static auto get()
-    {
-        if constexpr (R > 8) return f32_stream_col2_kernel<R>;
-        else return f32_stream_col_kernel<R>;
-    }
-    static constexpr int fallback_ctas() { if constexpr (R > 8) return 3; else return FColGeom<R>::CTAS; }
-};
-
 template <int R>
 cudaError_t launch_fstream(FStreamParams& p, const F32Taps& t, cudaStream_t s)
 {
@@ -320,30 +152,7 @@ cudaError_t launch_fstream(FStreamParams& p, const F32Taps& t, cudaStream_t s)
         f32_stream_row_kernel<R><<<(unsigned)((groups + FROW_THREADS - 1) / FROW_THREADS), FROW_THREADS, 0, s>>>(p);
         return cudaGetLastError();
     }
-    static const int per_sm = [] {
-        int n = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, ColKernel<R>::get(), 128, 0) != cudaSuccess || n < 1)
-            n = ColKernel<R>::fallback_ctas();
-        return n;
-    }();
-    const int sms = cached_sm_count();
-    // segment length: whole waves of the resident CTA slots, least halo re-reading (2R rows per segment)
-    const int64_t slots = (int64_t)sms * per_sm, cols = p.outer * p.xblocks;
-    double best = 1e300;
-    int best_seg = p.n_out;
-    for (int seg = 8; ; seg += 8) {
-        const int sg = seg < p.n_out ? seg : p.n_out;
-        const int64_t nseg = (p.n_out + sg - 1) / sg;
-        const int64_t waves = (cols * nseg + slots - 1) / slots;
-        const double cost = (double)waves * (sg + 2 * R + 8);
-        if (cost < best) { best = cost; best_seg = sg; }
-        if (seg >= p.n_out || seg >= 4096) break;
-    }
-    p.seg = best_seg;
-    if ((p.n_out + p.seg - 1) / p.seg > 65535) p.seg = (int32_t)((p.n_out + 65534) / 65535);
-    dim3 grid((unsigned)cols, (unsigned)((p.n_out + p.seg - 1) / p.seg));
-    ColKernel<R>::get()<<<grid, 128, 0, s>>>(p);
-    return cudaGetLastError();
+    return cudaErrorInvalidValue;       // column passes run on the tile kernel (f32_1d.cu)
 }
 
 }  // namespace
@@ -357,20 +166,13 @@ bool f32_stream_supported(const F32Line& g, int radius)
     // element-wise halo gather in the edge threads the 17-tap row pass took 0.352), column pass 0.170 / 0.19 /
     // 0.252 vs 0.23 / 0.24 / 0.27; 25 / 33 taps 0.34-0.67 vs 0.30-0.35: radius 12 / 16 stay on the tiles.
     if (g.n_in <= 0 || g.n_out <= 0 || g.outer <= 0 || g.inner <= 0) return false;
-    // radius 9..16: the ROW kernel wins over the shared-memory tile (33 taps on 512^3: 0.290 vs 0.356 ms); the packed
-    // column kernel does not (0.59 vs 0.34 ms: ptxas sinks its prefetch ring next to the consumers — 62 % long-
-    // scoreboard stalls even with volatile loads), so wide column passes stay on the tiles
-    if (R > 8 && g.inner != 1) return false;
+    // contiguous-axis passes only: the row kernel wins over the shared-memory tile at every radius (33 taps on 512^3:
+    // 0.299 vs 0.356 ms); strided-axis passes run on the tile kernel of f32_1d.cu
+    if (g.inner != 1) return false;
     const uintptr_t a = reinterpret_cast<uintptr_t>(g.in) | reinterpret_cast<uintptr_t>(g.out);
-    if (g.inner == 1) {
-        if (a & 3) return false;
-        const int64_t groups = g.outer * ((g.n_out + FROW_P - 1) / FROW_P);
-        if ((groups + FROW_THREADS - 1) / FROW_THREADS > 2147483647LL) return false;
-    } else {
-        const int C = fcols(R);
-        if (g.inner % C != 0 || (a & (uintptr_t)(4 * C - 1))) return false;
-        if (g.outer * ((g.inner / C + 127) / 128) > 2147483647LL) return false;
-    }
+    if (a & 3) return false;
+    const int64_t groups = g.outer * ((g.n_out + FROW_P - 1) / FROW_P);
+    if ((groups + FROW_THREADS - 1) / FROW_THREADS > 2147483647LL) return false;
     return true;
 }
 
@@ -385,13 +187,9 @@ cudaError_t launch_f32_stream(const F32Line& g, const F32Taps& t, cudaStream_t s
     p.cval = g.cval;
     p.seg = 0; p.xblocks = 0; p.gpr = 0; p.row_aligned = 0;
     const int R = fstream_bucket(t.radius);
-    if (g.inner == 1) {
-        p.gpr = (g.n_out + FROW_P - 1) / FROW_P;
-        const uintptr_t a = reinterpret_cast<uintptr_t>(g.in) | reinterpret_cast<uintptr_t>(g.out);
-        p.row_aligned = ((a & 15) == 0 && g.n_in % 4 == 0 && g.n_out % 4 == 0) ? 1 : 0;
-    } else {
-        p.xblocks = (int32_t)((g.inner / fcols(R) + 127) / 128);
-    }
+    p.gpr = (g.n_out + FROW_P - 1) / FROW_P;
+    const uintptr_t a = reinterpret_cast<uintptr_t>(g.in) | reinterpret_cast<uintptr_t>(g.out);
+    p.row_aligned = ((a & 15) == 0 && g.n_in % 4 == 0 && g.n_out % 4 == 0) ? 1 : 0;
     switch (R) {
     case 1: return launch_fstream<1>(p, t, s);
     case 2: return launch_fstream<2>(p, t, s);

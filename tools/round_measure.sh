@@ -1,7 +1,7 @@
 #!/bin/bash
 # One-GPU measurement session of a round: bench lines, launch list, ncu captures, config timings.
 # Usage (on the GPU box, from the repo root): bash tools/round_measure.sh <round-tag>
-R=${1:-r1}
+R=${1:-r2}
 O=gpurun_out
 mkdir -p $O
 python bench.py --impl reference --steps 3 --warmup 1 > $O/${R}_bench_reference_arm.json 2> $O/${R}_bench_reference_arm.err
@@ -10,16 +10,26 @@ python tools/time_configs.py > $O/${R}_config_timings.txt 2>/dev/null
 python tools/time_c3.py >> $O/${R}_config_timings.txt 2>/dev/null
 python tools/time_gradmag.py >> $O/${R}_config_timings.txt 2>/dev/null
 python tools/time_f32_1d.py >> $O/${R}_config_timings.txt 2>/dev/null
+python tools/time_c5_parts.py >> $O/${R}_config_timings.txt 2>/dev/null
 python tools/time_e2e.py 32 >> $O/${R}_config_timings.txt 2>/dev/null
 python tools/time_fused.py 512 2.0 reflect constant nearest mirror wrap >> $O/${R}_config_timings.txt 2>/dev/null
+python tools/time_at_size.py > $O/${R}_time_at_size.txt 2>/dev/null
+python tools/clock_probe.py 512 2.0 reflect 2.0 > $O/${R}_clock_probe.txt 2>/dev/null
+python tools/clock_probe.py 512 1.5 reflect 2.0 grad >> $O/${R}_clock_probe.txt 2>/dev/null
 # launch list of the bench command (cold-cache, serialised: shares, not absolutes)
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/${R}_ncu_launch_list_bench.csv \
-    python bench.py --steps 5 --warmup 3 --no-cpu > /dev/null 2>&1
-# full capture of the headline kernel and of the C3 streaming kernels
-ncu --set full --clock-control none --import-source on -k regex:fused3d --launch-skip 2 -c 1 -f -o $O/${R}_prof_fused \
+    python bench.py --steps 5 --warmup 3 --no-cpu --no-legs > /dev/null 2>&1
+# full captures: the headline kernel, the single-launch gradient magnitude, C5's three passes, C3's streaming kernels
+ncu --set full --clock-control none --import-source on -k regex:fws_kernel --launch-skip 2 -c 1 -f -o $O/${R}_prof_fused \
     python tools/prof_fused.py 512 2.0 reflect > /dev/null 2>&1
+ncu --set full --clock-control none --import-source on -k regex:fws_kernel --launch-skip 2 -c 1 -f -o $O/${R}_prof_grad \
+    python tools/prof_grad.py > /dev/null 2>&1
+ncu --set full --clock-control none --import-source on -k regex:corr1d_f32\|f32_stream --launch-skip 6 -c 3 -f -o $O/${R}_prof_c5 \
+    python tools/prof_c5.py > /dev/null 2>&1
 ncu --set full --clock-control none --import-source on -k regex:exact_stream --launch-skip 4 -c 2 -f -o $O/${R}_prof_c3_stream \
     python tools/prof_c3.py > /dev/null 2>&1
 python tools/ncu_summary.py $O/${R}_prof_fused.ncu-rep > $O/${R}_fused_gaussian512_reflect_ncu_summary.txt 2>&1
+python tools/ncu_summary.py $O/${R}_prof_grad.ncu-rep > $O/${R}_gradmag512_ncu_summary.txt 2>&1
+python tools/ncu_summary.py $O/${R}_prof_c5.ncu-rep > $O/${R}_c5_passes_ncu_summary.txt 2>&1
 python tools/ncu_summary.py $O/${R}_prof_c3_stream.ncu-rep > $O/${R}_c3_stream_ncu_summary.txt 2>&1
-tail -c 1500 $O/${R}_bench_n1.json
+tail -c 600 $O/${R}_bench_n1.json
