@@ -76,6 +76,7 @@ EXPORTS = (
     "sepfilt_version", "sepfilt_last_error", "sepfilt_correlate1d", "sepfilt_separable_f32",
     "sepfilt_separable_f32_supported", "sepfilt_gradmag_step", "sepfilt_copy_cast", "sepfilt_correlate_nd",
     "sepfilt_last_launch_count", "sepfilt_separable_f32_halo", "sepfilt_stream_write32", "sepfilt_stream_write32x2", "sepfilt_stream_wait32_geq",
+    "sepfilt_multiply", "sepfilt_ssim_map",
 )
 
 _lib = None
@@ -119,6 +120,10 @@ def lib():
         L.sepfilt_stream_write32.restype = ci
         L.sepfilt_stream_write32x2.argtypes = [vp, vp, vp, ctypes.c_uint32]
         L.sepfilt_stream_write32x2.restype = ci
+        L.sepfilt_multiply.argtypes = [vp, vp, vp, i64, ci, vp]
+        L.sepfilt_multiply.restype = ci
+        L.sepfilt_ssim_map.argtypes = [vp, vp, vp, vp, vp, vp, vp, ci, ctypes.POINTER(i64), ci, dbl, dbl, dbl, ci, vp]
+        L.sepfilt_ssim_map.restype = ci
         L.sepfilt_stream_wait32_geq.argtypes = [vp, vp, ctypes.c_uint32]
         L.sepfilt_stream_wait32_geq.restype = ci
         L.sepfilt_gradmag_step.argtypes = [vp, vp, i64, ci, ci, vp]

@@ -405,6 +405,28 @@ int sepfilt_separable_f32(const sepfilt_tensor* in, const sepfilt_tensor* out,
 
 int sepfilt_last_launch_count(void) { return g_last_launches; }
 
+int sepfilt_multiply(const void* a, const void* b, void* out, int64_t n, int dtype, void* stream)
+{
+    if (!a || !b || !out || n < 0) return fail(SEPFILT_ERR_INVALID, "bad multiply arguments");
+    if (dtype != SEPFILT_F32 && dtype != SEPFILT_F64) return fail(SEPFILT_ERR_UNSUPPORTED, "multiply takes float32 / float64");
+    cudaError_t e = launch_multiply(a, b, out, n, dtype, static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return fail_cuda(e, "multiply launch");
+    return SEPFILT_OK;
+}
+
+int sepfilt_ssim_map(const void* ux, const void* uy, const void* uxx, const void* uyy, const void* uxy,
+                     void* S, double* sum, int ndim, const int64_t* shape, int pad,
+                     double cov_norm, double C1, double C2, int dtype, void* stream)
+{
+    if (!ux || !uy || !uxx || !uyy || !uxy || !sum || !shape) return fail(SEPFILT_ERR_INVALID, "bad ssim_map arguments");
+    if (ndim < 1 || ndim > 3 || pad < 0) return fail(SEPFILT_ERR_INVALID, "ssim_map takes 1 to 3 dimensions");
+    if (dtype != SEPFILT_F32 && dtype != SEPFILT_F64) return fail(SEPFILT_ERR_UNSUPPORTED, "ssim_map takes float32 / float64");
+    cudaError_t e = launch_ssim_map(ux, uy, uxx, uyy, uxy, S, sum, ndim, shape, pad, cov_norm, C1, C2, dtype,
+                                    static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return fail_cuda(e, "ssim_map launch");
+    return SEPFILT_OK;
+}
+
 int sepfilt_separable_f32_halo(const sepfilt_tensor* in, const sepfilt_tensor* out,
                                const sepfilt_pass* passes, int npasses,
                                const sepfilt_pass* dpasses, int gradient_magnitude,

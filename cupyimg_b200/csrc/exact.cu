@@ -167,7 +167,7 @@ cudaError_t launch_exact_corr1d(const ExactParams& p, cudaStream_t s)
 // ---- generic_gradient_magnitude epilogue in the output dtype (filters.py:1187-1201) ----
 template <typename T>
 __global__ void __launch_bounds__(256)
-gradmag_step_kernel(T* __restrict__ acc, const T* __restrict__ a, int64_t n, int dtype, int op)
+gradmag_step_kernel(T* acc, const T* a, int64_t n, int dtype, int op)   // acc may alias a (ops 0 / 2 are unary)
 {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {

@@ -111,4 +111,10 @@ bool        fused_ws_supported(const FusedVolume& v, const F32Taps taps[3], cons
 cudaError_t launch_fused_ws(const FusedVolume& v, const F32Taps taps[3], const F32Taps dtaps[3],
                             bool gradmag, cudaStream_t s);
 
+// ---- elementwise stages of the skimage-level consumers (consumers.cu) ----
+cudaError_t launch_multiply(const void* a, const void* b, void* out, int64_t n, int dtype, cudaStream_t s);
+cudaError_t launch_ssim_map(const void* ux, const void* uy, const void* uxx, const void* uyy, const void* uxy,
+                            void* S, double* sum, int ndim, const int64_t* shape, int pad, double cov_norm,
+                            double C1, double C2, int dtype, cudaStream_t s);
+
 }  // namespace sepfilt

@@ -199,6 +199,21 @@ SEPFILT_API int sepfilt_stream_write32(void* stream, void* addr, uint32_t value)
 SEPFILT_API int sepfilt_stream_write32x2(void* stream, void* addr_a, void* addr_b, uint32_t value);
 SEPFILT_API int sepfilt_stream_wait32_geq(void* stream, void* addr, uint32_t value);
 
+/*
+ * Elementwise stages of the skimage-level callers of the separable filters (float32 / float64, contiguous,
+ * n elements; every operation separately rounded in the array dtype like the reference's cupy ufunc calls):
+ *  sepfilt_multiply: out = a * b — the products SSIM filters (skimage/metrics/_structural_similarity.py:203-207:
+ *      im1 * im1, im2 * im2, im1 * im2) and the structure tensor (skimage/feature/corner.py:131-134: der0 * der1);
+ *      out may alias a or b.
+ *  sepfilt_ssim_map: the SSIM map S = (A1 * A2) / (B1 * B2) of _structural_similarity.py:208-224 from the five
+ *      filtered arrays, written to S (may be NULL) and summed in float64 over crop(S, pad) (:226-230) into *sum
+ *      (device memory, zeroed by the caller) — one pass instead of ~20 elementwise kernels.  ndim <= 3.
+ */
+SEPFILT_API int sepfilt_multiply(const void* a, const void* b, void* out, int64_t n, int dtype, void* stream);
+SEPFILT_API int sepfilt_ssim_map(const void* ux, const void* uy, const void* uxx, const void* uyy, const void* uxy,
+                     void* S, double* sum, int ndim, const int64_t* shape, int pad,
+                     double cov_norm, double C1, double C2, int dtype, void* stream);
+
 /* Kernels enqueued by the calling thread's last successful sepfilt_separable_f32 call (1, or one per
  * axis when the gradient magnitude runs as accumulating launches): lets the host layer report
  * launch counts instead of assuming them. */
