@@ -7,6 +7,7 @@
 // (_util.py:170-228), then the C-cast store — bit-exact integer outputs, bit-identical float64.  Any (in, out)
 // dtype pair, any byte strides, up to SEPFILT_MAX_NDIM dimensions.  One output element per thread
 // (grid-stride); the boundary rule is evaluated only for threads whose footprint leaves the array.
+#include <cstdlib>
 #include <type_traits>
 #include "common.cuh"
 #include "kernels.h"
@@ -104,6 +105,129 @@ correlate_2d_kernel(const __grid_constant__ CorrNdParams p, const int ny, const 
     }
 }
 
+// ---- tile kernel for small 2-D weights (kh, kw <= 7: 3x3, 5x5, 7x7 ... on images or stacks of images) ----
+// The per-pixel kernel above converts every element to float64 once per TAP (9 .. 49 times) and walks the taps
+// with runtime loops.  Here a CTA stages the (32 + kh - 1) x (128 + KW - 1) footprint of a 128 x 32 output tile
+// in shared memory AS FLOAT64 — every element is loaded, boundary-mapped and converted exactly once — and a
+// thread then owns a 4 x 4 block of outputs: one row of its window (4 + KW - 1 doubles, LDS.128) feeds up to
+// 4 output rows x KW taps x 4 columns of DMUL + DADD from registers.  Same arithmetic and the same order of
+// operations per output as NI_Correlate (ky outer, kx inner, taps with |w| <= DBL_EPSILON skipped): bit-exact.
+// The kernel width is rounded up to KW = 3 / 5 / 7 with zero taps on the right, which the skip rule drops.
+constexpr int CT_W = 128, CT_H = 32, CT_MAXK = 7;
+constexpr int CT_ODD = 36;                  // 16-byte chunk (2 doubles) c lives at (c >> 1) + (c & 1) * CT_ODD: a lane's
+                                            // window starts 2 chunks after its neighbour's, and with even / odd chunks
+                                            // in separate halves (4 mod 8 apart) the LDS.128 and the staging STS.64 of a
+                                            // warp touch consecutive chunks
+constexpr int CT_PITCH = 2 * (CT_ODD + (CT_W + CT_MAXK - 1) / 4 + 1);     // doubles per staged row
+constexpr double CT_EPS = 2.220446049250313e-16;
+
+__device__ __forceinline__ int ct_off(int ty, int tx)
+{
+    const int c = tx >> 1;
+    return ty * CT_PITCH + 2 * ((c >> 1) + (c & 1) * CT_ODD) + (tx & 1);
+}
+
+template <typename InT, int KW>
+__global__ void __launch_bounds__(256, 2)
+correlate_2d_tile_kernel(const __grid_constant__ CorrNdParams p, const int ny, const int nx, const int kh, const int kw,
+                         const int by, const int bx, const int64_t planes)
+{
+    constexpr int SW = CT_W + KW - 1;                         // staged columns
+    constexpr int NWC = (4 + KW - 1 + 1) / 2;                 // 16-byte chunks of a thread's window row
+    __shared__ __align__(16) double tile[(CT_H + CT_MAXK - 1) * CT_PITCH];
+    __shared__ double wsm[CT_MAXK * KW];
+    const int tid = threadIdx.x;
+    if (tid < kh * KW) {
+        const int ky = tid / KW, kx = tid - ky * KW;
+        wsm[tid] = kx < kw ? (p.wdev ? p.wdev[ky * kw + kx] : p.w[ky * kw + kx]) : 0.0;
+    }
+    const int x0 = blockIdx.x * CT_W, y0 = blockIdx.y * CT_H;
+    const int sh = CT_H + kh - 1;                             // staged rows
+    const int ys0 = y0 - by, xs0 = x0 - bx;                   // source coordinate of staged element (0, 0)
+    const bool interior = ys0 >= 0 && ys0 + sh <= ny && xs0 >= 0 && xs0 + SW <= nx;
+    const int total = sh * SW;
+    const int tx = tid & 31, tg = tid >> 5;
+    const int ox = x0 + 4 * tx, oy = y0 + 4 * tg;
+    const int osize = dtype_size(p.out_dtype);
+    const bool vec_out = (nx & 3) == 0 && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0 && ox + 3 < nx;
+
+    for (int64_t z = blockIdx.z; z < planes; z += gridDim.z) {
+        const InT* plane = reinterpret_cast<const InT*>(p.in) + z * (int64_t)ny * nx;
+        __syncthreads();                                      // the previous plane's tile is consumed; wsm is written
+        // ---- stage: every load of the thread is in flight before its first conversion (a tile is ~18 elements per
+        //      thread: 256 threads x 18 x 4 B = the bytes one SM must keep in flight to cover the DRAM latency)
+        constexpr int NIT = ((CT_H + CT_MAXK - 1) * SW + 255) / 256;
+        InT raw[NIT];
+        int off[NIT];                                         // destination inside the tile; -1: none, -2: cval
+#pragma unroll
+        for (int u = 0; u < NIT; ++u) {
+            const int e = tid + 256 * u;
+            off[u] = -1;
+            raw[u] = InT(0);
+            if (e < total) {
+                const int ty = e / SW, txs = e - ty * SW;
+                int sy = ys0 + ty, sx = xs0 + txs;
+                if (!interior) { sy = remap_index32(p.mode, sy, ny); sx = remap_index32(p.mode, sx, nx); }
+                off[u] = ct_off(ty, txs);
+                if (sy < 0 || sx < 0) off[u] |= 0x40000000;   // outside under mode constant
+                else raw[u] = plane[(int64_t)sy * nx + sx];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < NIT; ++u)
+            if (off[u] >= 0) tile[off[u] & 0xffffff] = (off[u] & 0x40000000) ? p.cval : (double)raw[u];
+        __syncthreads();
+        // ---- compute: 4 x 4 outputs per thread; input row r of the block feeds output rows i with ky = r - i
+        double acc[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+        const double* wrow = tile + (4 * tg) * CT_PITCH + 2 * tx;     // chunk 2 tx + m -> tx + (m >> 1) + (m & 1) CT_ODD
+        for (int r = 0; r < kh + 3; ++r, wrow += CT_PITCH) {
+            double win[2 * NWC];
+#pragma unroll
+            for (int m = 0; m < NWC; ++m) {
+                const double2 q = *reinterpret_cast<const double2*>(wrow + 2 * ((m >> 1) + (m & 1) * CT_ODD));
+                win[2 * m] = q.x; win[2 * m + 1] = q.y;
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int ky = r - i;
+                if (ky >= 0 && ky < kh) {
+#pragma unroll
+                    for (int kx = 0; kx < KW; ++kx) {
+                        const double w = wsm[ky * KW + kx];
+                        if (fabs(w) > CT_EPS) {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) acc[i][j] = __dadd_rn(acc[i][j], __dmul_rn(win[j + kx], w));
+                        }
+                    }
+                }
+            }
+        }
+        // ---- store under scipy's cast rules
+        char* obase = p.out + (z * (int64_t)ny * nx) * osize;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int y = oy + i;
+            if (y >= ny) break;
+            const int64_t eo = (int64_t)y * nx + ox;
+            if (vec_out && p.out_dtype == SEPFILT_F32) {
+                *reinterpret_cast<float4*>(obase + eo * 4) = make_float4(__double2float_rn(acc[i][0]), __double2float_rn(acc[i][1]),
+                                                                         __double2float_rn(acc[i][2]), __double2float_rn(acc[i][3]));
+            } else if (vec_out && p.out_dtype == SEPFILT_F64) {
+                *reinterpret_cast<double2*>(obase + eo * 8) = make_double2(acc[i][0], acc[i][1]);
+                *reinterpret_cast<double2*>(obase + eo * 8 + 16) = make_double2(acc[i][2], acc[i][3]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (ox + j < nx) store_cast(obase + (eo + j) * osize, p.out_dtype, acc[i][j]);
+            }
+        }
+    }
+}
+
 static bool contiguous_c(const CorrNdParams& p, const int64_t* stride, int esize)
 {
     int64_t expect = esize;
@@ -126,6 +250,17 @@ static bool try_launch_2d(const CorrNdParams& p, cudaStream_t s, cudaError_t* er
     if (ny * nx > 2147483647LL || ny > (1 << 30) || nx > (1 << 30)) return false;
     int64_t planes = 1;
     for (int d = 0; d < p.ndim - 2; ++d) planes *= p.shape[d];
+    const int kh = p.wshape[p.ndim - 2], kw = p.wshape[p.ndim - 1];
+    static const bool no_tile = getenv("SEPFILT_NO_CORR_TILE") != nullptr;      // A/B aid
+    if (!no_tile && kh <= CT_MAXK && kw <= CT_MAXK && (ny + CT_H - 1) / CT_H <= 65535) {
+        dim3 tgrid((unsigned)((nx + CT_W - 1) / CT_W), (unsigned)((ny + CT_H - 1) / CT_H), (unsigned)(planes < 65535 ? planes : 65535));
+        const int by = p.before[p.ndim - 2], bx = p.before[p.ndim - 1];
+        if (kw <= 3) correlate_2d_tile_kernel<InT, 3><<<tgrid, 256, 0, s>>>(p, (int)ny, (int)nx, kh, kw, by, bx, planes);
+        else if (kw <= 5) correlate_2d_tile_kernel<InT, 5><<<tgrid, 256, 0, s>>>(p, (int)ny, (int)nx, kh, kw, by, bx, planes);
+        else correlate_2d_tile_kernel<InT, 7><<<tgrid, 256, 0, s>>>(p, (int)ny, (int)nx, kh, kw, by, bx, planes);
+        *err = cudaGetLastError();
+        return true;
+    }
     if ((ny + 7) / 8 > 65535) return false;
     dim3 grid((unsigned)((nx + 31) / 32), (unsigned)((ny + 7) / 8), (unsigned)(planes < 65535 ? planes : 65535));
     correlate_2d_kernel<InT><<<grid, 256, 0, s>>>(p, (int)ny, (int)nx, p.wshape[p.ndim - 2], p.wshape[p.ndim - 1],

@@ -84,3 +84,32 @@ def test_correlate_nd_outputs_views_large_kernels_errors(ndi):
     for ax in range(3):
         b = ndi.correlate1d(b, k, axis=ax)
     assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("dtype", ["float32", "uint8", "uint16", "int32", "float64"])
+def test_correlate_2d_tile_kernel_multi_tile(dtype, ndi):
+    """Weights on the last two axes up to 7 x 7 take the shared-memory tile kernel (correlate_nd.cu): stacks and
+    images spanning several 128 x 32 tiles, ragged edges, every boundary mode, shifted origins, non-finite data."""
+    rng = np.random.default_rng(41)
+    for shape, ws in [((3, 70, 300), (1, 3, 3)), ((2, 45, 260), (1, 5, 5)), ((97, 131), (7, 7)), ((40, 516), (3, 6)),
+                      ((33, 129), (6, 2)), ((5, 4), (7, 7))]:
+        x = (rng.random(shape) * 200 - (0 if dtype[0] == "u" else 60)).astype(dtype)
+        if dtype[0] == "f":
+            x[(0,) * x.ndim] = np.inf
+            x[tuple(s // 2 for s in shape)] = np.nan
+        w = rng.standard_normal(ws)
+        w[(0,) * len(ws)] = 0.0
+        if len(ws) == 2 and ws[1] > 2:
+            w[ws[0] // 2, ws[1] - 1] = 0.0
+        xd = to_device(x)
+        for mode in ["reflect", "constant", "nearest", "mirror", "wrap"]:
+            for origin in (0, [-(s // 2) for s in ws], [(s - 1) // 2 for s in ws]):
+                want = oracle.correlate(x, w, mode=mode, cval=-1.5, origin=origin)
+                got = to_host(ndi.correlate(xd, w, mode=mode, cval=-1.5, origin=origin))
+                np.testing.assert_array_equal(got, want, err_msg="%s %s %s %s" % (shape, ws, mode, origin))
+    # another output dtype than the input's (scipy's cast rules in the store)
+    x = (rng.random((50, 300)) * 300).astype(dtype)
+    w = rng.standard_normal((3, 3))
+    for t_out in ("uint8", "float32", "float64", "int64"):
+        np.testing.assert_array_equal(to_host(ndi.correlate(to_device(x), w, output=np.dtype(t_out))),
+                                      oracle.correlate(x, w, output=np.dtype(t_out)), err_msg=t_out)
