@@ -5,7 +5,7 @@
 // register budgets.
 //
 // One CTA (12 warps) owns a 128 x TY column of the volume and marches along z.
-//   Y warps  (warps 0-3, one per SM sub-partition, 88-104 registers): take the next input plane from a
+//   Y warps  (warps 0-3, one per SM sub-partition, plus warp 11 on 14-row tiles; 72-104 registers): take the next input plane from a
 //            shared counter, wait for its TMA box (cp.async.bulk.tensor.3d, mbarrier complete_tx), run
 //            the y pass for ALL rows of the tile from registers (a lane owns 4 columns: every staged
 //            row is read from shared memory once; packed fma.rn.f32x2) and publish the y-filtered
@@ -64,21 +64,22 @@ __host__ __device__ constexpr int cmin(int a, int b) { return a < b ? a : b; }
 // R: radius (exact), CPT: columns per XZ thread (8: 16 threads per tile row, 4: 32), TYC: tile rows,
 // HAS_Z: z pass present, GRAD: gradient magnitude (2 y-filtered planes, 3 z accumulator sets)
 // YSPLIT: the Y warps filter the tile rows in this many chunks (fewer live accumulators, more row loads)
-// RP: an XZ thread owns CPT (= 4) columns of TWO adjacent rows and the y-filtered plane is stored with the rows of a
-//     pair interleaved, so that every x-pass operand is a ready-made (row a, row b) pair: no re-paired window copies
-template <int R_, int CPT_, int TYC_, bool HAS_Z_, bool GRAD_, int YREGS_, int XZREGS_, int YSPLIT_ = 1, bool RP_ = false, int NT_ = 384>
+template <int R_, int CPT_, int TYC_, bool HAS_Z_, bool GRAD_, int YREGS_, int XZREGS_, int YSPLIT_ = 1>
 struct WsCfg {
     static constexpr int R = R_, CPT = CPT_, TYC = TYC_, YREGS = YREGS_, XZREGS = XZREGS_, YSPLIT = YSPLIT_;
     static constexpr int YCH = TYC_ / YSPLIT_;                  // rows per chunk
-    static constexpr bool HAS_Z = HAS_Z_, GRAD = GRAD_, RP = RP_;
+    static constexpr bool HAS_Z = HAS_Z_, GRAD = GRAD_;
     static constexpr int TX = 128, TPR = TX / CPT;
-    static constexpr int NT = NT_, NYW = 4;
-    static constexpr int XROWS = RP ? TYC / 2 : TYC;            // rows of XZ threads
-    static constexpr int NXZW = (TPR * XROWS + 31) / 32;        // XZ warps with work (<= 8)
-    // a warp slot without XZ rows (14-row tiles: warp 11) runs as one more Y warp: it sits on the sub-partition that
-    // has one XZ warp less, and ncu shows the XZ warps waiting for y-filtered planes 22 % of their time
-    static constexpr int NYTOT = NT / 32 - NXZW;
-    static constexpr int LREGS = (65536 / NT) & ~7;             // registers per thread of the launch allocation
+    static constexpr int NT = 384, NYW = 4;
+    static constexpr int NXZW = (TPR * TYC + 31) / 32;          // XZ warps with work (<= 8)
+    // A warp slot without XZ rows (14-row tiles: warp 11) runs as one more Y warp.  ncu (round 2) showed the XZ
+    // warps waiting for y-filtered planes 22 % of their time — the Y warps are the critical path — and warp 11 sits
+    // on the sub-partition that has one XZ warp less: 512^3 sigma 2 reflect 0.310 -> 0.282 ms.  More warps do not
+    // fit: a sub-partition's register file holds 512 registers per lane (Y 104 + 2 x XZ 200 = 504).
+    // (Measured and rejected in the same session: an x pass on (row a, row b) pairs read from a row-interleaved
+    //  y plane — no re-paired window copies, 17 % fewer instructions overall, but the interleaving MOVs land on
+    //  the Y warps: 0.292 ms.)
+    static constexpr int NYTOT = NYW + (8 - NXZW);
     static constexpr int HL = rup4(R), PW = TX + 2 * HL, NCG = PW / 4;
     static constexpr int BOX_ROWS = TYC + 2 * R;
     static constexpr int NF = GRAD ? 2 : 1, NZF = GRAD ? 3 : 1;
@@ -93,11 +94,7 @@ struct WsCfg {
     static constexpr int ODD_OFF = SWZ ? ((NCG / 2 + 3) / 8) * 8 + 4 : 0;
     static constexpr int YPG = SWZ ? ODD_OFF + NCG / 2 : NCG;   // float4 groups per row
     static constexpr int YP = 4 * YPG;
-    // RP layout of a y-filtered plane: [row pair][16-byte group = 2 columns x 2 rows]; a thread's window is the
-    // groups 2 oct .. 2 oct + WIN / 2: even groups are stored first, odd groups from unit ODD2 on, so the lanes of a
-    // warp read (and the Y lanes write) consecutive 16-byte units
-    static constexpr int NG2 = PW / 2, ODD2 = (NG2 + 1) / 2, RPITCH = 4 * (ODD2 + NG2 / 2);
-    static constexpr int YSLOT = RP ? (TYC / 2) * RPITCH : NF * TYC * YP;
+    static constexpr int YSLOT = NF * TYC * YP;
     static constexpr int NY = 8;
     static constexpr int NR = cmin(12, (WS_SMEM_BUDGET - NY * YSLOT * 4 - 1024) / (RSLOT * 4));
     static constexpr size_t SMEM = sizeof(float) * ((size_t)NR * RSLOT + (size_t)NY * YSLOT) + 1024;
@@ -109,10 +106,9 @@ struct WsCfg {
     static_assert(NXZW <= 8 && NXZW >= 1, "XZ warps");
     // setmaxnreg moves registers inside the CTA's launch allocation: 12 warps x 168 (= 65536 / 384 rounded
     // down to 8); a budget beyond it makes setmaxnreg.inc wait forever
-    static_assert(NYTOT * YREGS_ + NXZW * XZREGS_ <= (NT / 32) * LREGS && NT % 32 == 0, "register budget exceeds the launch allocation");
+    static_assert(NYW * YREGS_ + 8 * XZREGS_ <= 12 * 168, "register budget exceeds the launch allocation");
     static_assert(TYC_ % YSPLIT_ == 0, "row chunks");
     static_assert(WS_SMEM_BUDGET >= (int)SMEM, "shared memory");
-    static_assert(!RP || (!GRAD && CPT == 4 && TYC % 2 == 0 && YSPLIT == 1 && RPP % 2 == 0), "row-pair layout");
 };
 
 template <bool SWZ, int ODD_OFF> __device__ __forceinline__ int ycol_offset(int c)
@@ -121,17 +117,6 @@ template <bool SWZ, int ODD_OFF> __device__ __forceinline__ int ycol_offset(int 
     if (!SWZ) return c;
     const int g = c >> 2;
     return 4 * ((g >> 1) + (g & 1) * ODD_OFF) + (c & 3);
-}
-
-// float offset, inside a y slot, of (tile row r [+ TYC per further plane], staged column c)
-template <class C> __device__ __forceinline__ int ycell(int r, int c)
-{
-    if constexpr (C::RP) {
-        const int g = c >> 1;
-        return (r >> 1) * C::RPITCH + 4 * ((g >> 1) + (g & 1) * C::ODD2) + 2 * (c & 1) + (r & 1);
-    } else {
-        return r * C::YP + ycol_offset<C::SWZ, C::ODD_OFF>(c);
-    }
 }
 
 template <class C>
@@ -190,7 +175,7 @@ fws_kernel(const __grid_constant__ WsParams p, const __grid_constant__ CUtensorM
         for (int i = lane; i < ncol; i += 32) {
             const int gx = i < left ? i - left : p.nx + (i - left);
             const int sx = remap_index32(p.mode_x, gx, p.nx);
-            coltab[i] = (gx - (x0 - HL)) | ((sx - (x0 - HL)) << 16);     // staged columns: destination | source << 16
+            coltab[i] = ycol_offset<SWZ, C::ODD_OFF>(gx - (x0 - HL)) | (ycol_offset<SWZ, C::ODD_OFF>(sx - (x0 - HL)) << 16);
         }
         if (lane == 0) {
             meta[0] = 0; meta[1] = 0;
@@ -236,7 +221,7 @@ fws_kernel(const __grid_constant__ WsParams p, const __grid_constant__ CUtensorM
             if (cfast && i < ncol * TYC * NF) {
                 const int r = i / ncol, c = i - r * ncol;
                 const int e = coltab[c];
-                cpatch[u] = ycell<C>(r, e & 0xffff) | (ycell<C>(r, e >> 16) << 16);
+                cpatch[u] = (r * YP + (e & 0xffff)) | ((r * YP + (e >> 16)) << 16);
             }
         }
         for (;;) {
@@ -278,25 +263,12 @@ fws_kernel(const __grid_constant__ WsParams p, const __grid_constant__ CUtensorM
                         }
                     }
                 }
-                if constexpr (C::RP) {
-                    // columns 4 lane .. 4 lane + 3 are groups 2 lane (unit lane) and 2 lane + 1 (unit ODD2 + lane)
-                    float* dst = yp + 4 * lane;
-#pragma unroll
-                    for (int o = 0; o + 1 < YCH; o += 2) {
-                        float a0, a1, a2, a3, b0, b1, b2, b3;
-                        unpack2(acc[0][o][0], a0, a1); unpack2(acc[0][o][1], a2, a3);
-                        unpack2(acc[0][o + 1][0], b0, b1); unpack2(acc[0][o + 1][1], b2, b3);
-                        *reinterpret_cast<float4*>(dst + (o >> 1) * C::RPITCH) = make_float4(a0, b0, a1, b1);
-                        *reinterpret_cast<float4*>(dst + (o >> 1) * C::RPITCH + 4 * C::ODD2) = make_float4(a2, b2, a3, b3);
-                    }
-                } else {
                 float* dst = yp + ycol_offset<SWZ, C::ODD_OFF>(4 * lane) + h * YCH * YP;
 #pragma unroll
                 for (int f = 0; f < NF; ++f)
 #pragma unroll
                     for (int o = 0; o < YCH; ++o)
                         *reinterpret_cast<ulonglong2*>(dst + (f * TYC + o) * YP) = make_ulonglong2(acc[f][o][0], acc[f][o][1]);
-                }
             }
             // ---- tail: staged columns [128, 128 + 2 HL): lane = (column pair, row part)
             {
@@ -319,23 +291,12 @@ fws_kernel(const __grid_constant__ WsParams p, const __grid_constant__ CUtensorM
                         }
                     }
                 }
-                if constexpr (C::RP) {
-                    // rows part RPP + o, + 1 (RPP and TYC are even) of columns 128 + 2 cp, + 1: one group
-#pragma unroll
-                    for (int o = 0; o + 1 < RPP; o += 2) {
-                        float a0, a1, b0, b1;
-                        unpack2(acc[0][o], a0, a1); unpack2(acc[0][o + 1], b0, b1);
-                        if (part * RPP + o < TYC)
-                            *reinterpret_cast<float4*>(yp + ycell<C>(part * RPP + o, 128 + 2 * cp)) = make_float4(a0, b0, a1, b1);
-                    }
-                } else {
                 float* dst = yp + ycol_offset<SWZ, C::ODD_OFF>(128 + 2 * cp);
 #pragma unroll
                 for (int f = 0; f < NF; ++f)
 #pragma unroll
                     for (int o = 0; o < RPP; ++o)
                         if (part * RPP + o < TYC) *reinterpret_cast<u64*>(dst + (f * TYC + part * RPP + o) * YP) = acc[f][o];
-                }
             }
             };
             if (ytab) ypass.template operator()<true>(); else ypass.template operator()<false>();
@@ -350,7 +311,7 @@ fws_kernel(const __grid_constant__ WsParams p, const __grid_constant__ CUtensorM
                 for (int i = lane; i < total; i += 32) {
                     const int r = i / ncol, c = i - r * ncol;
                     const int e = coltab[c];
-                    yp[ycell<C>(r, e & 0xffff)] = yp[ycell<C>(r, e >> 16)];
+                    yp[r * YP + (e & 0xffff)] = yp[r * YP + (e >> 16)];
                 }
                 __syncwarp();
             } else if (ncol) {
@@ -376,22 +337,15 @@ fws_kernel(const __grid_constant__ WsParams p, const __grid_constant__ CUtensorM
     // =============================== XZ warps ===============================
     reg_alloc<C::XZREGS>();
     const int t = tid - C::NYW * 32;
-    const int row = t / TPR, oct = t - row * TPR;               // RP: `row` counts row pairs
-    constexpr bool RP = C::RP;
-    const int ya = y0 + (RP ? 2 : 1) * row;                     // (first) array row of this thread
-    const bool in_tile = row < C::XROWS, col_ok = x0 + CPT * oct < p.nx;
-    const bool row_ok = in_tile && ya >= 0 && ya < p.ny;
-    const bool ok0 = row_ok && col_ok;
-    // second store of a thread: the next 4 columns (CPT 8) or the same columns of the pair's second row (RP)
-    const bool ok1 = RP ? (in_tile && ya + 1 >= 0 && ya + 1 < p.ny && col_ok) : (CPT == 8 && row_ok && x0 + CPT * oct + 4 < p.nx);
+    const int row = t / TPR, oct = t - row * TPR;
+    const bool row_ok = row < TYC && y0 + row >= 0 && y0 + row < p.ny;
+    const bool ok0 = row_ok && x0 + CPT * oct < p.nx;
+    const bool ok1 = CPT == 8 && row_ok && x0 + CPT * oct + 4 < p.nx;
     const size_t plane_elems = (size_t)p.ny * p.nx;
-    const int ya_c = min(max(ya, 0), p.ny - 1);
-    float* out_ptr = p.out + (size_t)zb * plane_elems + (size_t)ya_c * p.nx + x0 + CPT * oct;
-    const int second = RP ? (min(max(ya + 1, 0), p.ny - 1) - ya_c) * p.nx : 4;      // element offset of the second store
-    // window start inside a y plane
-    const int yoff = RP ? (in_tile ? row : 0) * C::RPITCH + 4 * oct : (in_tile ? row : 0) * YP + (SWZ ? 4 * oct : CPT * oct);
+    float* out_ptr = p.out + (size_t)zb * plane_elems + (size_t)min(max(y0 + row, 0), p.ny - 1) * p.nx + x0 + CPT * oct;
+    const int yoff = (row < TYC ? row : 0) * YP + (SWZ ? 4 * oct : CPT * oct);   // window start inside a y plane
 
-    constexpr int NP = RP ? CPT : CPT / 2;                      // packed pairs per thread: column pairs, or (row a, row b) per column
+    constexpr int NP = CPT / 2;                                 // packed column pairs per thread
     constexpr int ZS = C::ZS;
     u64 zacc[NZF][ZS][NP];
 #pragma unroll
@@ -473,24 +427,7 @@ fws_kernel(const __grid_constant__ WsParams p, const __grid_constant__ CUtensorM
             const float* yp = ybuf + ys * YSLOT + yoff;
             mbar_wait(&full_y[ys], par);
             u64 v[NZF][NP];
-            if constexpr (RP) {
-                // window: staged columns [CPT oct, CPT oct + CPT + 2 HL) of both rows, one packed pair per column
-                constexpr int W2 = CPT + 2 * HL;
-                u64 w2[W2];
-#pragma unroll
-                for (int m = 0; m < W2 / 2; ++m) {
-                    const ulonglong2 ld = *reinterpret_cast<const ulonglong2*>(yp + 4 * ((m >> 1) + (m & 1) * C::ODD2));
-                    w2[2 * m] = ld.x; w2[2 * m + 1] = ld.y;
-                }
-#pragma unroll
-                for (int j = 0; j < NP; ++j) v[0][j] = mul2s(w2[j + HL - R], p.wx[0]);
-#pragma unroll
-                for (int k = 1; k <= 2 * R; ++k)
-#pragma unroll
-                    for (int j = 0; j < NP; ++j) v[0][j] = fma2s(w2[j + HL - R + k], p.wx[k], v[0][j]);
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&empty_y[ys]);
-            } else {
+            {
                 float win[WIN];
                 u64 pe[WIN / 2], po[WIN / 2];
                 load_window(yp, win);
@@ -524,11 +461,8 @@ fws_kernel(const __grid_constant__ WsParams p, const __grid_constant__ CUtensorM
                     zscatter(NZF - 1, q, v[NZF - 1], p.wz);
                 }
                 if (idx >= 2 * R) {
-                    float res[2 * NP];
-                    if (RP) {
-#pragma unroll
-                        for (int c = 0; c < NP; ++c) unpack2(zacc[0][fs][c], res[c], res[NP + c]);
-                    } else if (!GRAD) {
+                    float res[CPT];
+                    if (!GRAD) {
 #pragma unroll
                         for (int c = 0; c < NP; ++c) unpack2(zacc[0][fs][c], res[2 * c], res[2 * c + 1]);
                     } else {
@@ -547,22 +481,17 @@ fws_kernel(const __grid_constant__ WsParams p, const __grid_constant__ CUtensorM
                         }
                     }
                     if (ok0) *reinterpret_cast<float4*>(out_ptr) = make_float4(res[0], res[1], res[2], res[3]);
-                    if ((CPT == 8 || RP) && ok1)
-                        *reinterpret_cast<float4*>(out_ptr + second) =
-                            make_float4(res[2 * NP - 4], res[2 * NP - 3], res[2 * NP - 2], res[2 * NP - 1]);
+                    if (CPT == 8 && ok1)
+                        *reinterpret_cast<float4*>(out_ptr + 4) = make_float4(res[CPT - 4], res[CPT - 3], res[CPT - 2], res[CPT - 1]);
                     out_ptr += plane_elems;
                 }
             } else {
-                float res[2 * NP];
+                float res[CPT];
 #pragma unroll
-                for (int c = 0; c < NP; ++c) {
-                    if (RP) unpack2(v[0][c], res[c], res[NP + c]);
-                    else unpack2(v[0][c], res[2 * c], res[2 * c + 1]);
-                }
+                for (int c = 0; c < NP; ++c) unpack2(v[0][c], res[2 * c], res[2 * c + 1]);
                 if (ok0) *reinterpret_cast<float4*>(out_ptr) = make_float4(res[0], res[1], res[2], res[3]);
-                if ((CPT == 8 || RP) && ok1)
-                    *reinterpret_cast<float4*>(out_ptr + second) =
-                        make_float4(res[2 * NP - 4], res[2 * NP - 3], res[2 * NP - 2], res[2 * NP - 1]);
+                if (CPT == 8 && ok1)
+                    *reinterpret_cast<float4*>(out_ptr + 4) = make_float4(res[CPT - 4], res[CPT - 3], res[CPT - 2], res[CPT - 1]);
                 out_ptr += plane_elems;
             }
         }
@@ -657,17 +586,8 @@ cudaError_t launch_plain(const FusedVolume& v, WsParams& p, int sms, cudaStream_
 {
     const WsPlan p16 = plan_tiles(v, R, HAS_Z, 16, sms), p14 = plan_tiles(v, R, HAS_Z, 14, sms);
     // cost is in row-planes; a 14-row tile does 14 / 16 of the work of a 16-row tile per plane
-    static const char* rp_env = getenv("SEPFILT_WS_RP");           // A/B aid: "1" = the row-pair x pass (fewer instructions, measured slower)
-    if (!rp_env || rp_env[0] != '1') {
-        static const char* nt_env = getenv("SEPFILT_WS_NT");        // A/B aid: 416 / 448 = 6 / 7 Y warps on 14-row tiles
-        const int nt = nt_env ? atoi(nt_env) : 384;
-        if (p14.cost < p16.cost && nt == 416) return launch_cfg<WsCfg<R, 8, 14, HAS_Z, false, 96, 200, 1, false, 416>>(v, p, p14, s);
-        if (p14.cost < p16.cost && nt == 448) return launch_cfg<WsCfg<R, 8, 14, HAS_Z, false, 88, 200, 1, false, 448>>(v, p, p14, s);
-        if (p14.cost < p16.cost) return launch_cfg<WsCfg<R, 8, 14, HAS_Z, false, 104, 200>>(v, p, p14, s);
-        return launch_cfg<WsCfg<R, 8, 16, HAS_Z, false, 104, 200>>(v, p, p16, s);
-    }
-    if (p14.cost < p16.cost) return launch_cfg<WsCfg<R, 4, 14, HAS_Z, false, 104, 200, 1, true>>(v, p, p14, s);
-    return launch_cfg<WsCfg<R, 4, 16, HAS_Z, false, 104, 200, 1, true>>(v, p, p16, s);
+    if (p14.cost < p16.cost) return launch_cfg<WsCfg<R, 8, 14, HAS_Z, false, 104, 200>>(v, p, p14, s);
+    return launch_cfg<WsCfg<R, 8, 16, HAS_Z, false, 104, 200>>(v, p, p16, s);
 }
 
 // gradient magnitude: 4 columns per XZ thread, 8 tile rows (three z accumulator sets per column)
