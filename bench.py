@@ -662,7 +662,7 @@ def run_ours(args):
                     "achieved": achieved, "peak": peak, "unit": "GB/s",
                     "frac": hbm_frac, "traffic": tr["dram_bytes_per_launch"] if tr else None,
                     "traffic_source": tr["source"] if tr else None,
-                    "kernel": "fused3d_f32 (1 launch per call)" if per_call_launches == 1 else
+                    "kernel": "fws_kernel (csrc/fused_ws.cu, warp-specialised fused y/x/z pass; 1 launch per call)" if per_call_launches == 1 else
                               "gaussian_filter call = %s launches (per-axis tiled passes)" % per_call_launches,
                     "kernel_ms": kernel_ms, "kernel_ms_single_launch_idle_gpu": kernel_ms_isolated,
                     "kernel_ms_sustained_blocks": {"median": statistics.median(blocks) if blocks else None,

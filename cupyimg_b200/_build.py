@@ -13,7 +13,7 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_PKG, "csrc")
 LIB_DIR = os.path.join(_PKG, "_lib")
 LIB_PATH = os.path.join(LIB_DIR, "libsepfilt_b200.so")
-SOURCES = ["api.cu", "correlate_nd.cu", "exact.cu", "exact_tiled.cu", "exact_stream.cu", "minmax_stream.cu", "f32_1d.cu", "f32_stream.cu", "fused3d.cu", "fused_ws.cu", "consumers.cu"]
+SOURCES = ["api.cu", "correlate_nd.cu", "exact.cu", "exact_tiled.cu", "exact_stream.cu", "minmax_stream.cu", "f32_1d.cu", "f32_stream.cu", "fused3d.cu", "fused_ws.cu", "fused_ws_p1.cu", "fused_ws_p2.cu", "fused_ws_w1.cu", "fused_ws_w2.cu", "fused_ws_g.cu", "consumers.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++20",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",

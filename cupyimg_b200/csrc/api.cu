@@ -376,8 +376,11 @@ int sepfilt_separable_f32_supported(const sepfilt_tensor* in, const sepfilt_tens
 {
     FusedVolume v;
     F32Taps taps[3], dtaps[3];
-    // derivative passes are only needed for their radius == smoothing radius here
-    return build_fused(in, out, passes, npasses, passes, gradient_magnitude, 0, cval, &v, taps, dtaps, false) == SEPFILT_OK;
+    // derivative passes are only needed for their radius == smoothing radius here.  The query is what the z-slab
+    // sharding asks before it relies on sepfilt_separable_f32_halo, so it answers for a launch WITH neighbour halos
+    sepfilt_halo with_halo;
+    std::memset(&with_halo, 0, sizeof with_halo);
+    return build_fused(in, out, passes, npasses, passes, gradient_magnitude, 0, cval, &v, taps, dtaps, false, &with_halo) == SEPFILT_OK;
 }
 
 int sepfilt_separable_f32(const sepfilt_tensor* in, const sepfilt_tensor* out,

@@ -7,6 +7,7 @@
 // (_util.py:170-228), then the C-cast store — bit-exact integer outputs, bit-identical float64.  Any (in, out)
 // dtype pair, any byte strides, up to SEPFILT_MAX_NDIM dimensions.  One output element per thread
 // (grid-stride); the boundary rule is evaluated only for threads whose footprint leaves the array.
+#include <cmath>
 #include <cstdlib>
 #include <type_traits>
 #include "common.cuh"
@@ -121,6 +122,13 @@ constexpr int CT_ODD = 36;                  // 16-byte chunk (2 doubles) c lives
 constexpr int CT_PITCH = 2 * (CT_ODD + (CT_W + CT_MAXK - 1) / 4 + 1);     // doubles per staged row
 constexpr double CT_EPS = 2.220446049250313e-16;
 
+// taps as kernel parameters in the padded [ky][KW] layout: every tap address and every skip test is a compile-time
+// offset into the constant bank (bit ky * KW + kx of `mask`: |w| > DBL_EPSILON, scipy's footprint)
+struct CtWeights {
+    double w[CT_MAXK * CT_MAXK];
+    unsigned long long mask;
+};
+
 __device__ __forceinline__ int ct_off(int ty, int tx)
 {
     const int c = tx >> 1;
@@ -129,18 +137,13 @@ __device__ __forceinline__ int ct_off(int ty, int tx)
 
 template <typename InT, int KW>
 __global__ void __launch_bounds__(256, 3)          // 3 CTAs / SM: 0.162 ms on 8 x 2048^2 f32 3x3 against 0.205 ms at 2
-correlate_2d_tile_kernel(const __grid_constant__ CorrNdParams p, const int ny, const int nx, const int kh, const int kw,
-                         const int by, const int bx, const int64_t planes)
+correlate_2d_tile_kernel(const __grid_constant__ CorrNdParams p, const __grid_constant__ CtWeights cw, const int ny, const int nx,
+                         const int kh, const int by, const int bx, const int64_t planes)
 {
     constexpr int SW = CT_W + KW - 1;                         // staged columns
     constexpr int NWC = (4 + KW - 1 + 1) / 2;                 // 16-byte chunks of a thread's window row
     __shared__ __align__(16) double tile[(CT_H + CT_MAXK - 1) * CT_PITCH];
-    __shared__ double wsm[CT_MAXK * KW];
     const int tid = threadIdx.x;
-    if (tid < kh * KW) {
-        const int ky = tid / KW, kx = tid - ky * KW;
-        wsm[tid] = kx < kw ? (p.wdev ? p.wdev[ky * kw + kx] : p.w[ky * kw + kx]) : 0.0;
-    }
     const int x0 = blockIdx.x * CT_W, y0 = blockIdx.y * CT_H;
     const int sh = CT_H + kh - 1;                             // staged rows
     const int ys0 = y0 - by, xs0 = x0 - bx;                   // source coordinate of staged element (0, 0)
@@ -149,16 +152,47 @@ correlate_2d_tile_kernel(const __grid_constant__ CorrNdParams p, const int ny, c
     const int tx = tid & 31, tg = tid >> 5;
     const int ox = x0 + 4 * tx, oy = y0 + 4 * tg;
     const int osize = dtype_size(p.out_dtype);
+    constexpr int VEC = 16 / (int)sizeof(InT);                // elements per 16-byte staging load
+    constexpr int NVR = (SW + VEC - 1) / VEC + 1;             // aligned vectors that cover a staged row at any phase
+    constexpr int NITV = ((CT_H + CT_MAXK - 1) * NVR + 255) / 256;
+    const bool vec_in = interior && nx % VEC == 0 && (reinterpret_cast<uintptr_t>(p.in) & 15) == 0;
     const bool vec_out = (nx & 3) == 0 && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0 && ox + 3 < nx;
 
     for (int64_t z = blockIdx.z; z < planes; z += gridDim.z) {
         const InT* plane = reinterpret_cast<const InT*>(p.in) + z * (int64_t)ny * nx;
-        __syncthreads();                                      // the previous plane's tile is consumed; wsm is written
+        __syncthreads();                                      // the previous plane's tile is consumed
         // ---- stage.  Interior tiles: every load of the thread is in flight before its first conversion (a tile is
         //      ~18 elements per thread; no branch sits between the loads, so ptxas keeps them batched — with the
         //      boundary rule inline every F2F waited for its own load: 53 % long-scoreboard stalls, 0.378 ms)
         constexpr int NIT = ((CT_H + CT_MAXK - 1) * SW + 255) / 256;
-        if (interior) {
+        if (vec_in) {
+            // 16-byte loads from the aligned range that covers the staged columns: a quarter of the load instructions
+            // and of the index arithmetic of the element-wise path below (VEC elements per load)
+            const int a0 = xs0 & ~(VEC - 1), shift = xs0 - a0;
+            const InT* src = plane + (int64_t)ys0 * nx + a0;
+            uint4 raw[NITV];
+#pragma unroll
+            for (int u = 0; u < NITV; ++u) {
+                const int e = tid + 256 * u;
+                const int ty = e / NVR, vi = e - ty * NVR;
+                raw[u] = make_uint4(0u, 0u, 0u, 0u);
+                if (ty < sh && vi * VEC < shift + SW) raw[u] = *reinterpret_cast<const uint4*>(src + ty * nx + vi * VEC);
+            }
+#pragma unroll
+            for (int u = 0; u < NITV; ++u) {
+                const int e = tid + 256 * u;
+                const int ty = e / NVR, vi = e - ty * NVR;
+                InT el[VEC];
+                *reinterpret_cast<uint4*>(el) = raw[u];
+                if (ty < sh) {
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) {
+                        const int c = vi * VEC + v - shift;
+                        if (c >= 0 && c < SW) tile[ct_off(ty, c)] = (double)el[v];
+                    }
+                }
+            }
+        } else if (interior) {
             const InT* src = plane + (int64_t)ys0 * nx + xs0;
             InT raw[NIT];
 #pragma unroll
@@ -189,23 +223,27 @@ correlate_2d_tile_kernel(const __grid_constant__ CorrNdParams p, const int ny, c
 #pragma unroll
             for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
         const double* wrow = tile + (4 * tg) * CT_PITCH + 2 * tx;     // chunk 2 tx + m -> tx + (m >> 1) + (m & 1) CT_ODD
-        for (int r = 0; r < kh + 3; ++r, wrow += CT_PITCH) {
-            double win[2 * NWC];
+        const unsigned long long mask = cw.mask;
 #pragma unroll
-            for (int m = 0; m < NWC; ++m) {
-                const double2 q = *reinterpret_cast<const double2*>(wrow + 2 * ((m >> 1) + (m & 1) * CT_ODD));
-                win[2 * m] = q.x; win[2 * m + 1] = q.y;
-            }
+        for (int r = 0; r < 4 + CT_MAXK - 1; ++r) {
+            if (r < kh + 3) {                                 // rows beyond the kernel height are not staged
+                double win[2 * NWC];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int ky = r - i;
-                if (ky >= 0 && ky < kh) {
+                for (int m = 0; m < NWC; ++m) {
+                    const double2 q = *reinterpret_cast<const double2*>(wrow + r * CT_PITCH + 2 * ((m >> 1) + (m & 1) * CT_ODD));
+                    win[2 * m] = q.x; win[2 * m + 1] = q.y;
+                }
 #pragma unroll
-                    for (int kx = 0; kx < KW; ++kx) {
-                        const double w = wsm[ky * KW + kx];
-                        if (fabs(w) > CT_EPS) {
+                for (int i = 0; i < 4; ++i) {
+                    const int ky = r - i;                     // compile time; rows ky >= kh have no mask bits
+                    if (ky >= 0 && ky < CT_MAXK) {
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) acc[i][j] = __dadd_rn(acc[i][j], __dmul_rn(win[j + kx], w));
+                        for (int kx = 0; kx < KW; ++kx) {
+                            if ((mask >> (ky * KW + kx)) & 1ull) {
+                                const double w = cw.w[ky * KW + kx];
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) acc[i][j] = __dadd_rn(acc[i][j], __dmul_rn(win[j + kx], w));
+                            }
                         }
                     }
                 }
@@ -257,12 +295,21 @@ static bool try_launch_2d(const CorrNdParams& p, cudaStream_t s, cudaError_t* er
     for (int d = 0; d < p.ndim - 2; ++d) planes *= p.shape[d];
     const int kh = p.wshape[p.ndim - 2], kw = p.wshape[p.ndim - 1];
     static const bool no_tile = getenv("SEPFILT_NO_CORR_TILE") != nullptr;      // A/B aid
-    if (!no_tile && kh <= CT_MAXK && kw <= CT_MAXK && (ny + CT_H - 1) / CT_H <= 65535) {
+    if (!no_tile && !p.wdev && kh <= CT_MAXK && kw <= CT_MAXK && (ny + CT_H - 1) / CT_H <= 65535) {
         dim3 tgrid((unsigned)((nx + CT_W - 1) / CT_W), (unsigned)((ny + CT_H - 1) / CT_H), (unsigned)(planes < 65535 ? planes : 65535));
         const int by = p.before[p.ndim - 2], bx = p.before[p.ndim - 1];
-        if (kw <= 3) correlate_2d_tile_kernel<InT, 3><<<tgrid, 256, 0, s>>>(p, (int)ny, (int)nx, kh, kw, by, bx, planes);
-        else if (kw <= 5) correlate_2d_tile_kernel<InT, 5><<<tgrid, 256, 0, s>>>(p, (int)ny, (int)nx, kh, kw, by, bx, planes);
-        else correlate_2d_tile_kernel<InT, 7><<<tgrid, 256, 0, s>>>(p, (int)ny, (int)nx, kh, kw, by, bx, planes);
+        const int KWT = kw <= 3 ? 3 : kw <= 5 ? 5 : 7;
+        CtWeights cw;
+        cw.mask = 0;
+        for (int ky = 0; ky < CT_MAXK; ++ky)
+            for (int kx = 0; kx < KWT; ++kx) {
+                const double w = (ky < kh && kx < kw) ? p.w[ky * kw + kx] : 0.0;
+                cw.w[ky * KWT + kx] = w;
+                if (std::fabs(w) > CT_EPS) cw.mask |= 1ull << (ky * KWT + kx);
+            }
+        if (KWT == 3) correlate_2d_tile_kernel<InT, 3><<<tgrid, 256, 0, s>>>(p, cw, (int)ny, (int)nx, kh, by, bx, planes);
+        else if (KWT == 5) correlate_2d_tile_kernel<InT, 5><<<tgrid, 256, 0, s>>>(p, cw, (int)ny, (int)nx, kh, by, bx, planes);
+        else correlate_2d_tile_kernel<InT, 7><<<tgrid, 256, 0, s>>>(p, cw, (int)ny, (int)nx, kh, by, bx, planes);
         *err = cudaGetLastError();
         return true;
     }

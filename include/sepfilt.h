@@ -219,7 +219,8 @@ SEPFILT_API int sepfilt_ssim_map(const void* ux, const void* uy, const void* uxx
  * launch counts instead of assuming them. */
 SEPFILT_API int sepfilt_last_launch_count(void);
 
-/* Would sepfilt_separable_f32 accept this request?  1 yes, 0 no (no error is set). */
+/* Would sepfilt_separable_f32_halo (and therefore sepfilt_separable_f32) accept this request?  1 yes, 0 no (no error
+ * is set).  Answers for a launch with neighbour halos: the z-slab sharding asks before it relies on the halo launch. */
 SEPFILT_API int sepfilt_separable_f32_supported(const sepfilt_tensor* in, const sepfilt_tensor* out,
                                     const sepfilt_pass* passes, int npasses,
                                     int gradient_magnitude, double cval);

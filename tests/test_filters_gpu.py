@@ -429,22 +429,44 @@ def test_host_pipeline_matches_resident_filter(ndi):
 
 @pytest.mark.parametrize("mode", ["reflect", "constant", "nearest", "mirror", "wrap"])
 def test_f32_radius_9_to_16(mode, ndi):
-    """sigma 2.5 .. 4 (radius 10 .. 16).  3-D volumes: three single-axis passes (the fused kernel keeps no z state
-    at that radius; z pass + fused y/x was measured at 1.04 ms against 1.02 ms on 512^3 and dropped).
-    Stacks of 2-D images (no z pass): two single-axis passes as well (the fused 2-D kernel for radius 12 / 16 was
+    """sigma 2.25 .. 4 (radius 9 .. 16).  3-D volumes: ONE launch of the warp-specialised fused kernel on 8-row tiles
+    (fused_ws.cuh, round 2; before: three single-axis passes), except `wrap` along y / x (far-side sources: per-axis
+    passes).  Stacks of 2-D images (no z pass): two single-axis passes (the fused 2-D kernel for radius 12 / 16 was
     dropped when the single-axis passes overtook it: 0.54 against 0.71 ms for sigma (0, 4, 4) on 512^3)."""
     from cupyimg_b200 import _ffi
     rng = np.random.default_rng(33)
-    for shape, sig, launches in [((40, 52, 64), lambda s: s, 3), ((12, 70, 200), lambda s: (0, s, s), 2)]:
+    fused = 1 if mode != "wrap" else 3
+    for shape, sig, launches in [((40, 52, 64), lambda s: s, fused), ((33, 70, 132), lambda s: s, fused),
+                                 ((12, 70, 200), lambda s: (0, s, s), 2)]:
         x = rng.random(shape).astype(np.float32)
         xd = to_device(x)
-        for sigma in (2.5, 3.0, 4.0):
+        for sigma in (2.25, 2.5, 2.75, 3.0, 3.25, 3.5, 3.75, 4.0):
             want = oracle.gaussian_filter(x, sig(sigma), mode=mode)
             _ffi.LAUNCHES = 0
             got = to_host(ndi.gaussian_filter(xd, sig(sigma), mode=mode))
-            # wrap along y / x is declined by the fused kernel (far-side sources): per-axis passes
-            expect = launches
-            assert _ffi.LAUNCHES == expect, (shape, sigma, _ffi.LAUNCHES)
+            assert _ffi.LAUNCHES == launches, (shape, sigma, _ffi.LAUNCHES)
+            assert_f32_close(got, want, atol_scale=2e-6)
+
+
+@pytest.mark.parametrize("mode", ["reflect", "constant", "nearest", "mirror"])
+def test_fused_ws_every_radius(mode, ndi):
+    """Every radius 1 .. 8 of the warp-specialised fused kernel (14- / 16-row tiles, fifth Y warp) on shapes with ragged
+    tile edges, against the oracle; uniform (box) taps as well as gaussian ones."""
+    from cupyimg_b200 import _ffi
+    rng = np.random.default_rng(77)
+    for shape in [(20, 45, 132), (9, 30, 64), (35, 14, 260)]:
+        x = rng.random(shape).astype(np.float32)
+        xd = to_device(x)
+        for radius in range(1, 9):
+            sigma = radius / 4.0
+            want = oracle.gaussian_filter(x, sigma, mode=mode)
+            _ffi.LAUNCHES = 0
+            got = to_host(ndi.gaussian_filter(xd, sigma, mode=mode))
+            assert _ffi.LAUNCHES == 1, (shape, radius, _ffi.LAUNCHES)
+            assert_f32_close(got, want, atol_scale=2e-6)
+            size = 2 * radius + 1
+            want = oracle.uniform_filter(x, size, mode=mode)
+            got = to_host(ndi.uniform_filter(xd, size, mode=mode))
             assert_f32_close(got, want, atol_scale=2e-6)
 
 
