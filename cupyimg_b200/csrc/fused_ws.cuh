@@ -107,7 +107,10 @@ struct WsCfg {
     static_assert(NXZW <= 8 && NXZW >= 1, "XZ warps");
     // setmaxnreg moves registers inside the CTA's launch allocation: 12 warps x 168 (= 65536 / 384 rounded
     // down to 8); a budget beyond it makes setmaxnreg.inc wait forever
-    static_assert(NYW * YREGS_ + 8 * XZREGS_ <= 12 * 168, "register budget exceeds the launch allocation");
+    static_assert(NYTOT * YREGS_ + NXZW * XZREGS_ <= 12 * 168, "register budget exceeds the launch allocation");
+    // ... and registers only move inside an SM sub-partition (warps w, w + 4, w + 8: one Y and two XZ warps, 3 x 168 at
+    // launch): Y 112 / XZ 200 passes the CTA-wide test above and hangs in setmaxnreg.inc (measured: a 15-minute timeout)
+    static_assert(NXZW < 5 || YREGS_ + 2 * XZREGS_ <= 3 * 168, "register budget exceeds the sub-partition's launch allocation");
     static_assert(TYC_ % YSPLIT_ == 0, "row chunks");
     static_assert(WS_SMEM_BUDGET >= (int)SMEM, "shared memory");
 };
@@ -225,6 +228,8 @@ fws_kernel(const __grid_constant__ WsParams p, const __grid_constant__ CUtensorM
                 cpatch[u] = (r * YP + (e & 0xffff)) | ((r * YP + (e >> 16)) << 16);
             }
         }
+        // (Measured and rejected: reading the plane counter one plane ahead to hide the atomic's latency — a reserved
+        //  but unstarted plane stalls the in-order XZ warps: 512^3 sigma 2 0.287 -> 0.298 ms.)
         for (;;) {
             int pl = 0;
             if (lane == 0) pl = atomicAdd(&meta[0], 1);
