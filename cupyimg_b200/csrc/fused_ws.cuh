@@ -79,7 +79,9 @@ struct WsCfg {
     // fit: a sub-partition's register file holds 512 registers per lane (Y 104 + 2 x XZ 200 = 504).
     // (Measured and rejected in the same session: an x pass on (row a, row b) pairs read from a row-interleaved
     //  y plane — no re-paired window copies, 17 % fewer instructions overall, but the interleaving MOVs land on
-    //  the Y warps: 0.292 ms.)
+    //  the Y warps: 0.292 ms.  The same x pass in the gradient-magnitude kernel, whose XZ warps bind (140 -> 34 MOV per
+    //  two planes): 0.709 -> 0.728 ms on 512^3 sigma 1.5 — the instruction count is not what limits these kernels, the
+    //  dependent FFMA2 chains of 2-3 resident warps per sub-partition are.)
     static constexpr int NYTOT = NYW + (8 - NXZW);
     static constexpr int HL = rup4(R), PW = TX + 2 * HL, NCG = PW / 4;
     static constexpr int BOX_ROWS = TYC + 2 * R;
