@@ -22,10 +22,9 @@ bool fused_ws_supported(const FusedVolume& v, const F32Taps taps[3], const F32Ta
         // plain filters, every radius 1 .. 16.  Radius <= 8: 14- / 16-row tiles, 8 columns per XZ thread — 512^3 reflect
         // sigma 1 / 1.5 / 2: 0.192 / 0.237 / 0.282 ms against 0.228 / 0.289 / 0.330 ms on fused3d.  Radius 9 .. 16 (sigma
         // 2.25 .. 4): 8-row tiles, 4 columns per thread — sigma 2.5 / 3 / 4 0.531 / 0.599 / 0.738 ms against 0.595 / 0.641 /
-        // 0.761 ms for three single-axis passes; those tiles re-read a (8 + 2R)-row box per 8 output rows and are not
-        // used with neighbour halos
+        // 0.761 ms for three single-axis passes; those tiles re-read a (8 + 2R)-row box per 8 output rows, so with
+        // neighbour halos the z-slab sharding hands them LOCAL pads (sharded.py, "pull1"), never planes across NVLink
         if (!has_z || r < 1 || r > WS_MAXR) return false;
-        if (r > 8 && v.halo) return false;
     }
     if (v.nx % 4 != 0 || (reinterpret_cast<uintptr_t>(v.in) & 15) || (reinterpret_cast<uintptr_t>(v.out) & 15))
         return false;

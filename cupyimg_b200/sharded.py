@@ -29,7 +29,7 @@ from . import _array, _ffi
 from .scipy.ndimage import filters as _filters
 
 # flag slots of the peer-memory protocol (32-bit words in each rank's symmetric flag array)
-_LO_READY, _HI_READY, _LO_DONE, _HI_DONE, _CTA_COUNTER = 0, 1, 2, 3, 8
+_LO_READY, _HI_READY, _LO_DONE, _HI_DONE, _LO_PAD, _HI_PAD, _CTA_COUNTER = 0, 1, 2, 3, 4, 5, 8
 
 
 def batch_range(n_items, world_size, rank):
@@ -162,7 +162,11 @@ class ZSlabFilter:
         mine = self._flag_ptrs[self.rank]
         # the warp-specialised kernel (gradient magnitude) waits for a neighbour's flag only when its march reaches
         # that neighbour's planes and spreads the reads over its z segments: in place is faster there
-        mode = self.p2p_mode if self.p2p_mode != "auto" else ("direct" if dspecs is not None else "pull")
+        # plain filters of radius > 8 (8-row tiles that re-read a tall box, a long pipeline fill): two boundary strips cost
+        # 40 % of a 256-plane slab there, so the pads are pulled as above but ONE launch covers the whole slab and waits
+        # for each pad's flag only when its march reaches that pad ("pull1")
+        wide = dspecs is None and max(sp.radius() for sp in specs) > 8
+        mode = self.p2p_mode if self.p2p_mode != "auto" else ("direct" if dspecs is not None else ("pull1" if wide else "pull"))
         grad = 1 if dspecs is not None else 0
         # my slab is complete at this point of the stream: tell the ranks that read it (one batched memop)
         _ffi.check(L.sepfilt_stream_write32x2(
@@ -217,8 +221,22 @@ class ZSlabFilter:
                 cs = _array.current_stream(self.device)
                 _ffi.check(L.sepfilt_stream_wait32_geq(cs, mine + 4 * slot, epoch))
                 pad.copy_(peer_planes, non_blocking=True)
+                if mode == "pull1":                                  # the pad is filled: the kernel may read it
+                    _ffi.check(L.sepfilt_stream_write32(cs, mine + 4 * (_LO_PAD if slot == _LO_READY else _HI_PAD), epoch))
                 # the neighbour's planes have been read: it may overwrite its slab
                 _ffi.check(L.sepfilt_stream_write32(cs, self._flag_ptrs[peer] + 4 * done_slot, epoch))
+        if mode == "pull1":
+            halo = _ffi.Halo()
+            halo.epoch = epoch
+            if self.has_lo:
+                halo.lo, halo.planes_lo, halo.ready_lo = self._pad_lo.data_ptr(), r, mine + 4 * _LO_PAD
+            if self.has_hi:
+                halo.hi, halo.planes_hi, halo.ready_hi = self._pad_hi.data_ptr(), r, mine + 4 * _HI_PAD
+            ok = halo_launch(self.slab, output, halo, 0)
+            if ok:                                   # (the next step's pulls wait for this launch: side.wait_stream(main) above)
+                self.last_backend = ("peer memory: copy engines pull the neighbour planes over NVLink into local pads; ONE launch "
+                                     "reads them when its march gets there (flag written behind each copy)")
+            return ok
         z0 = r if self.has_lo else 0
         z1 = nz - r if self.has_hi else nz
         ok = True

@@ -37,7 +37,7 @@ def _halo_call(x, lo, hi, out, specs, dspecs=None, flags=None, epoch=0, done=Non
 
 
 @pytest.mark.parametrize("mode", ["reflect", "constant", "nearest", "mirror"])
-@pytest.mark.parametrize("sigma,grad", [(2.0, False), (1.0, False), (1.25, False), (1.5, True), (0.75, True)])
+@pytest.mark.parametrize("sigma,grad", [(2.0, False), (1.0, False), (1.25, False), (2.5, False), (4.0, False), (1.5, True), (0.75, True)])
 def test_halo_call_equals_concatenated_volume(mode, sigma, grad):
     from cupyimg_b200 import _array, _ffi
     from cupyimg_b200.scipy import ndimage as ndi
@@ -80,9 +80,11 @@ def test_halo_call_declines_what_it_cannot_fuse():
     # halo thinner than the z radius
     specs = F._gaussian_specs(probe, 2.0, 0, "reflect", 4.0)
     assert _halo_call(x, lo, None, out, specs) == _ffi.ERR_UNSUPPORTED
-    # radius 16 has no fused kernel with a z pass
-    specs = F._gaussian_specs(probe, 4.0, 0, "reflect", 4.0)
-    assert _halo_call(x, torch.rand((16, 64, 64), device="cuda"), None, out, specs) == _ffi.ERR_UNSUPPORTED
+    # radius 20 (sigma 5) has no fused kernel; `wrap` along y / x is declined at every radius
+    specs = F._gaussian_specs(probe, 5.0, 0, "reflect", 4.0)
+    assert _halo_call(x, torch.rand((20, 64, 64), device="cuda"), None, out, specs) == _ffi.ERR_UNSUPPORTED
+    specs = F._gaussian_specs(probe, 2.0, 0, "wrap", 4.0)
+    assert _halo_call(x, torch.rand((8, 64, 64), device="cuda"), None, out, specs) == _ffi.ERR_UNSUPPORTED
 
 
 def test_stream_flag_operations():

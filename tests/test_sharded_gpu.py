@@ -35,7 +35,7 @@ def _worker(rank, world, port, result_dir, backend):
         vol = torch.rand((nz * world, ny, nx), generator=g)
         ok = True
         for mode in ["reflect", "wrap", "constant", "mirror", "nearest"]:
-            for sigma, radius in [(2.0, 8), (1.0, 4)]:
+            for sigma, radius in [(2.0, 8), (1.0, 4), (2.5, 10), (4.0, 16)]:
                 want = ndi.gaussian_filter(vol.to(dev), sigma, mode=mode)
                 x = vol[rank * nz:(rank + 1) * nz].to(dev)
                 plan = sharded.ZSlabFilter(x.shape, radius=radius, mode=mode, device=dev, backend=backend)

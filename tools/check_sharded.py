@@ -23,6 +23,8 @@ for backend in ["p2p", "nccl"]:
         for name, radius, fs, fp in [
                 ("gauss2", 8, lambda: ndi.gaussian_filter(vol, 2.0, mode=mode), lambda p: p.gaussian_filter(x, 2.0)),
                 ("gauss1", 4, lambda: ndi.gaussian_filter(vol, 1.0, mode=mode), lambda p: p.gaussian_filter(x, 1.0)),
+                ("gauss2.5", 10, lambda: ndi.gaussian_filter(vol, 2.5, mode=mode), lambda p: p.gaussian_filter(x, 2.5)),
+                ("gauss4", 16, lambda: ndi.gaussian_filter(vol, 4.0, mode=mode), lambda p: p.gaussian_filter(x, 4.0)),
                 ("uniform5", 4, lambda: ndi.uniform_filter(vol, 5, mode=mode), lambda p: p.uniform_filter(x, 5)),
                 ("gradmag1.5", 6, lambda: ndi.gaussian_gradient_magnitude(vol, 1.5, mode=mode), lambda p: p.gaussian_gradient_magnitude(x, 1.5)),
                 ("sobel0", 1, lambda: ndi.sobel(vol, 0, mode=mode), lambda p: p.sobel(x, 0))]:
