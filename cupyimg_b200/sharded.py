@@ -20,6 +20,7 @@ The reference is single-GPU (no collectives anywhere); this
 B200 scale-out of its per-axis loops (filters.py:651-662, :777-789).
 """
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -167,6 +168,8 @@ class ZSlabFilter:
         # for each pad's flag only when its march reaches that pad ("pull1")
         wide = dspecs is None and max(sp.radius() for sp in specs) > 8
         mode = self.p2p_mode if self.p2p_mode != "auto" else ("direct" if dspecs is not None else ("pull1" if wide else "pull"))
+        if dspecs is None and os.environ.get("SEPFILT_P2P_PLAIN"):      # A/B aid: pull / pull1 / direct for the plain filters
+            mode = os.environ["SEPFILT_P2P_PLAIN"]
         grad = 1 if dspecs is not None else 0
         # my slab is complete at this point of the stream: tell the ranks that read it (one batched memop)
         _ffi.check(L.sepfilt_stream_write32x2(
