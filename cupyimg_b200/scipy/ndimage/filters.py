@@ -534,7 +534,14 @@ def _gaussian_spec(axis, sigma, order, mode_code, truncate, radius=None):
         lw = radius
     if not isinstance(lw, numbers.Integral) or lw < 0:
         raise ValueError("Radius must be a nonnegative integer.")
-    return _PassSpec(axis, _gaussian_taps_cached(sd, int(order), int(lw)), 0, mode_code)
+    return _gaussian_pass_cached(int(axis), sd, int(order), int(lw), int(mode_code))
+
+
+@functools.lru_cache(maxsize=512)
+def _gaussian_pass_cached(axis, sigma, order, radius, mode_code):
+    """One immutable pass spec per (axis, sigma, order, radius, mode): its ctypes struct is built once, so a loop that
+    calls the same filter (a benchmark, a sharded step) spends no host time on taps."""
+    return _PassSpec(axis, _gaussian_taps_cached(sigma, order, radius), 0, mode_code)
 
 
 def gaussian_filter1d(input, sigma, axis=-1, order=0, output=None, mode="reflect", cval=0.0,
