@@ -16,7 +16,7 @@ PARAM_TAPS = 129
 MAX_TAPS = 4096
 FAST_MAX_RADIUS = 16
 
-OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_SCRATCH, ERR_CUDA = 0, -1, -2, -3, -4
+OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_SCRATCH, ERR_CUDA, ERR_VALUE = 0, -1, -2, -3, -4, -5
 ACC_F64_EXACT, ACC_F32 = 0, 1
 
 MODE_CODES = {
@@ -147,9 +147,9 @@ def check(rc):
     if rc == OK:
         return
     msg = last_error()
+    if rc == ERR_VALUE:                  # axis / origin out of range: ValueError in the reference
+        raise ValueError(msg)
     if rc == ERR_INVALID:
-        if "origin" in msg or "axis" in msg:
-            raise ValueError(msg)
         raise RuntimeError(msg)
     if rc == ERR_UNSUPPORTED:
         raise NotImplementedError(msg)

@@ -85,11 +85,11 @@ bool c_contiguous(const sepfilt_tensor* t)
 int check_pass(const sepfilt_pass* p, int ndim)
 {
     if (!p) return fail(SEPFILT_ERR_INVALID, "pass is NULL");
-    if (p->axis < 0 || p->axis >= ndim) return fail(SEPFILT_ERR_INVALID, "invalid axis %d", p->axis);
+    if (p->axis < 0 || p->axis >= ndim) return fail(SEPFILT_ERR_VALUE, "invalid axis %d", p->axis);
     if (p->ntaps < 1 || p->ntaps > SEPFILT_MAX_TAPS)
         return fail(SEPFILT_ERR_INVALID, "filter length %d not in 1..%d", p->ntaps, SEPFILT_MAX_TAPS);
     const int before = p->ntaps / 2 + p->origin;
-    if (before < 0 || before >= p->ntaps) return fail(SEPFILT_ERR_INVALID, "invalid origin");
+    if (before < 0 || before >= p->ntaps) return fail(SEPFILT_ERR_VALUE, "invalid origin");
     if (p->mode < SEPFILT_REFLECT || p->mode > SEPFILT_WRAP)
         return fail(SEPFILT_ERR_INVALID, "boundary mode not supported");
     if (!p->uniform && !p->taps) return fail(SEPFILT_ERR_INVALID, "no filter weights given");
@@ -150,7 +150,7 @@ int sepfilt_correlate1d(const sepfilt_tensor* in, const sepfilt_tensor* out,
         return fail(SEPFILT_ERR_INVALID, "unknown accumulator policy %d", acc);
     const int64_t total = numel(out);
     if (total == 0) return SEPFILT_OK;
-    if (in->shape[pass->axis] < 1) return fail(SEPFILT_ERR_INVALID, "input is empty along the filtered axis");
+    if (in->shape[pass->axis] < 1) return fail(SEPFILT_ERR_VALUE, "input is empty along the filtered axis");
     if (!in->ptr || !out->ptr) return fail(SEPFILT_ERR_INVALID, "NULL data pointer");
 
     DeviceGuard guard(in->device);
@@ -544,7 +544,7 @@ int sepfilt_correlate_nd(const sepfilt_tensor* in, const sepfilt_tensor* out,
         if (in->shape[d] != out->shape[d]) return fail(SEPFILT_ERR_INVALID, "output shape not correct");
         if (wshape[d] < 1) return fail(SEPFILT_ERR_INVALID, "filter weights array has incorrect shape");
         const int before = wshape[d] / 2 + origin[d];
-        if (before < 0 || before >= wshape[d]) return fail(SEPFILT_ERR_INVALID, "invalid origin");
+        if (before < 0 || before >= wshape[d]) return fail(SEPFILT_ERR_VALUE, "invalid origin");
         K *= wshape[d];
         if (K > SEPFILT_MAX_TAPS) return fail(SEPFILT_ERR_INVALID, "more than %d filter weights", SEPFILT_MAX_TAPS);
         p.shape[d] = in->shape[d];

@@ -48,10 +48,13 @@ extern "C" {
 
 typedef enum {
     SEPFILT_OK = 0,
-    SEPFILT_ERR_INVALID = -1,      /* bad argument (NULL, rank, axis, K, origin, mode, dtype) */
+    SEPFILT_ERR_INVALID = -1,      /* bad argument (NULL, rank, K, mode, dtype) */
     SEPFILT_ERR_UNSUPPORTED = -2,  /* valid request this entry point has no kernel for */
     SEPFILT_ERR_SCRATCH = -3,      /* scratch buffer missing or too small */
-    SEPFILT_ERR_CUDA = -4          /* a CUDA runtime / driver call failed */
+    SEPFILT_ERR_CUDA = -4,         /* a CUDA runtime / driver call failed */
+    SEPFILT_ERR_VALUE = -5         /* an axis or origin out of range: the argument errors for which the reference raises
+                                      ValueError (_util.py / _filters_core.py:63-76) rather than RuntimeError — the class
+                                      travels in the status code, not in the message text */
 } sepfilt_status;
 
 /* element types: the 10 numeric types the reference tests sweep
