@@ -625,6 +625,14 @@ def _accumulate(acc, a, op):
     _ffi.count_launch()
 
 
+def _is_component_view(a):
+    """True for a real DevArray carved out of a complex owner (DevArray.component)."""
+    try:
+        return a.dtype.kind != "c" and _array.to_numpy_dtype(a.obj.dtype).kind == "c"
+    except Exception:
+        return False
+
+
 def _generic_axis_reduce(input, derivative, output, mode, cval, extra_arguments, extra_keywords, magnitude):
     """Shared body of generic_laplace (sum of per-axis results, filters.py:1011-1038) and
     generic_gradient_magnitude (sqrt of the sum of squares, filters.py:1173-1204); all
@@ -648,7 +656,9 @@ def _generic_axis_reduce(input, derivative, output, mode, cval, extra_arguments,
             _copy_cast(inp, out)
         return _array.export(out, inp)
     modes = _normalize_sequence(mode, ndim)
-    acc = out if out.c_contiguous() else _array.empty(out.shape, out.dtype, out.device)
+    # the derivative callable is handed an array OBJECT: a real / imaginary component view has none of its own (its
+    # owner is the complex array, and a size-1 view even counts as contiguous), so it accumulates in a temporary
+    acc = out if out.c_contiguous() and not _is_component_view(out) else _array.empty(out.shape, out.dtype, out.device)
     derivative(input, 0, acc.obj, modes[0], cval, *extra_arguments, **extra_keywords)
     if magnitude:
         _accumulate(acc, acc, 0)

@@ -110,3 +110,14 @@ def test_complex_output_rules_and_errors(ndi):
     # empty
     e = torch.empty((0, 4), dtype=torch.complex64, device="cuda")
     assert ndi.correlate1d(e, w).shape == (0, 4)
+
+
+def test_laplace_of_a_size_one_complex_array(ndi):
+    """A size-1 component view counts as contiguous; the per-axis accumulation must still not write through the
+    complex owner."""
+    for shape in [(1,), (1, 1), (1, 1, 1)]:
+        x = np.full(shape, 1.5 - 2.5j, dtype=np.complex64)
+        got = host(ndi.laplace(dev(x)))
+        want = oracle.laplace(x.real.copy()) + 1j * oracle.laplace(x.imag.copy())
+        assert got.dtype == np.complex64 and got.shape == shape
+        np.testing.assert_allclose(got, want, rtol=1e-6, atol=1e-6)
