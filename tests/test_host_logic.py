@@ -128,3 +128,43 @@ def test_window_filter_specs():
     assert not F._fused_candidate(a, b, [mx, F._PassSpec(2, None, 0, 0, uniform=F._MAX, size=3)], False)
     with pytest.raises(NotImplementedError):
         F._check_minmax_cval(float("nan"))
+
+
+def test_gaussian_pass_specs_are_cached_and_immutable():
+    """One pass spec (and one ctypes struct) per (axis, sigma, order, radius, mode): a loop that calls the same filter
+    spends no host time on taps; the cached taps cannot be written through."""
+    a = F._gaussian_spec(1, 2.0, 0, F._check_mode("reflect"), 4.0)
+    b = F._gaussian_spec(1, np.float64(2.0), 0, F._check_mode("reflect"), 4.0)
+    assert a is b and a.struct()[0] is b.struct()[0]
+    assert F._gaussian_spec(1, 2.0, 1, F._check_mode("reflect"), 4.0) is not a          # another order
+    assert F._gaussian_spec(0, 2.0, 0, F._check_mode("reflect"), 4.0) is not a          # another axis
+    assert F._gaussian_spec(1, 2.0, 0, F._check_mode("mirror"), 4.0) is not a           # another mode
+    assert F._gaussian_spec(1, 2.0, 0, F._check_mode("reflect"), 4.0, radius=5).size == 11
+    assert a.size == 17 and a.radius() == 8
+    with pytest.raises(ValueError):
+        a.taps[0] = 1.0
+    with pytest.raises(ValueError):
+        F._gaussian_spec(1, 2.0, 0, F._check_mode("reflect"), 4.0, radius=-1)
+
+
+def test_status_codes_carry_the_exception_class():
+    """include/sepfilt.h: SEPFILT_ERR_VALUE -> ValueError, SEPFILT_ERR_UNSUPPORTED -> NotImplementedError, the rest
+    RuntimeError (the class no longer depends on the message text)."""
+    assert (_ffi.OK, _ffi.ERR_INVALID, _ffi.ERR_UNSUPPORTED, _ffi.ERR_SCRATCH, _ffi.ERR_CUDA, _ffi.ERR_VALUE) == (0, -1, -2, -3, -4, -5)
+    _ffi.check(_ffi.OK)
+    for rc, exc in [(_ffi.ERR_VALUE, ValueError), (_ffi.ERR_UNSUPPORTED, NotImplementedError),
+                    (_ffi.ERR_INVALID, RuntimeError), (_ffi.ERR_SCRATCH, RuntimeError), (_ffi.ERR_CUDA, RuntimeError)]:
+        with pytest.raises(exc):
+            _ffi.check(rc)
+    header = open(__import__("os").path.join(__import__("os").path.dirname(__file__), "..", "include", "sepfilt.h")).read()
+    assert "SEPFILT_ERR_VALUE = -5" in header
+
+
+def test_component_view_detection():
+    class Owner:
+        dtype = np.dtype("complex64")
+    c = _array.DevArray(0, (1,), (8,), np.complex64, 0, Owner())
+    assert F._is_component_view(c.component(0)) and F._is_component_view(c.component(1))
+    assert not F._is_component_view(c)
+    assert c.component(0).c_contiguous()            # why contiguity alone is not enough for a size-1 array
+    assert not F._is_component_view(_array.DevArray(0, (4,), (4,), np.float32, 0, None))
