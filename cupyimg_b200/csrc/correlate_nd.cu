@@ -182,7 +182,7 @@ correlate_2d_tile_kernel(const __grid_constant__ CorrNdParams p, const __grid_co
             for (int u = 0; u < NITV; ++u) {
                 const int e = tid + 256 * u;
                 const int ty = e / NVR, vi = e - ty * NVR;
-                InT el[VEC];
+                alignas(16) InT el[VEC];
                 *reinterpret_cast<uint4*>(el) = raw[u];
                 if (ty < sh) {
 #pragma unroll
