@@ -488,7 +488,7 @@ def uniform_filter(input, size=3, output=None, mode="reflect", cval=0.0, origin=
     for a, sz, og, md in zip(axes, sizes, origins, modes):
         if sz > 1:
             sz = int(sz)
-            specs.append(_PassSpec(a, None, _check_origin(og, sz), _check_mode(md), uniform=True, size=sz))
+            specs.append(_uniform_pass_cached(int(a), sz, int(_check_origin(og, sz)), int(_check_mode(md))))
     _run_passes(inp, out, specs, cval, dtype_mode)
     return _array.export(out, inp)
 
@@ -535,6 +535,12 @@ def _gaussian_spec(axis, sigma, order, mode_code, truncate, radius=None):
     if not isinstance(lw, numbers.Integral) or lw < 0:
         raise ValueError("Radius must be a nonnegative integer.")
     return _gaussian_pass_cached(int(axis), sd, int(order), int(lw), int(mode_code))
+
+
+@functools.lru_cache(maxsize=512)
+def _uniform_pass_cached(axis, size, origin, mode_code):
+    """Like :func:`_gaussian_pass_cached` for the mean window of ``uniform_filter``."""
+    return _PassSpec(axis, None, origin, mode_code, uniform=True, size=size)
 
 
 @functools.lru_cache(maxsize=512)
